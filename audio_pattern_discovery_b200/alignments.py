@@ -1,0 +1,276 @@
+"""Host-side mirror of the reference's src/alignments.rs on top of libapd_b200.
+
+Same names, argument meaning and failure behaviour as the Rust surface
+(file:line relative to the reference repository):
+
+    AlignmentWorkers::new(data)            src/alignments.rs:17-26
+    AlignmentWorkers::align_all(&discover) src/alignments.rs:31-67
+    AlignmentWorkers.result                src/alignments.rs:13   (n*n row-major f32)
+    AlignmentParams{..}, ::default(len)    src/alignments.rs:77-94
+    Alignment::new / construct_alignment / score   src/alignments.rs:106-180
+
+Everything numeric runs in the CUDA library through the C ABI of include/apd.h;
+this file is plumbing only and fails loudly if the library or a GPU is missing.
+"""
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _capi
+from ._capi import APD_MODE_FAST, APD_MODE_STRICT, ApdError, apd_params, apd_stats  # noqa: F401
+from .spectrogram import NDSequence
+
+_u32p = C.POINTER(C.c_uint32)
+_fp = C.POINTER(C.c_float)
+
+
+class AlignmentParams:
+    """src/alignments.rs:77-83"""
+
+    def __init__(self, warping_band, insertion_penalty=1.0, deletion_penalty=1.0, match_penalty=1.0):
+        self.warping_band = int(warping_band)
+        self.insertion_penalty = float(insertion_penalty)
+        self.deletion_penalty = float(deletion_penalty)
+        self.match_penalty = float(match_penalty)
+
+    @staticmethod
+    def default(len):  # noqa: A002  (the reference's argument name)
+        """src/alignments.rs:86-93"""
+        return AlignmentParams(len, 1.0, 1.0, 1.0)
+
+    def __repr__(self):
+        return ("AlignmentParams { warping_band: %d, insertion_penalty: %r, deletion_penalty: %r, "
+                "match_penalty: %r }" % (self.warping_band, self.insertion_penalty,
+                                         self.deletion_penalty, self.match_penalty))
+
+
+def _c_params(pct, ins, dele, mat, mode):
+    return apd_params(float(pct), float(ins), float(dele), float(mat), int(mode))
+
+
+class Context:
+    """One device context (apd_ctx): owns the packed sequence arena on one GPU."""
+
+    def __init__(self, device=0):
+        self._lib = _capi.lib()
+        h = C.c_void_p()
+        st = self._lib.apd_create(int(device), C.byref(h))
+        if st != _capi.APD_OK:
+            msg = self._lib.apd_last_error(None)
+            raise ApdError(st, msg.decode() if msg else "")
+        self._h = h
+        self.device = int(device)
+        self.n = 0
+        self.dim = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.apd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, st):
+        _capi.check(self._h, st)
+
+    # -- sequence packing ------------------------------------------------------
+    def set_sequences(self, seqs, dim=None):
+        """seqs: list of (T, D) float32 arrays (or NDSequence).  Copies them to the device."""
+        arrs = []
+        for s in seqs:
+            if isinstance(s, NDSequence):
+                a = s.as_array()
+            else:
+                a = np.ascontiguousarray(s, dtype=np.float32)
+                if a.ndim == 1:
+                    a = a.reshape(-1, 1)
+            arrs.append(a)
+        n = len(arrs)
+        if dim is None:
+            dim = arrs[0].shape[1] if n else 1
+        for a in arrs:
+            if a.shape[0] and a.shape[1] != dim:
+                raise ValueError("all sequences must share the frame width")
+        ptrs = (_fp * max(n, 1))()
+        for k, a in enumerate(arrs):
+            ptrs[k] = a.ctypes.data_as(_fp)
+        lens = np.array([a.shape[0] for a in arrs], dtype=np.uint32)
+        self._check(self._lib.apd_set_sequences(self._h, ptrs, lens.ctypes.data_as(_u32p), n, dim))
+        self.n, self.dim = n, dim
+
+    def set_sequences_flat(self, flat, offsets, lens, dim):
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        self._check(self._lib.apd_set_sequences_flat(
+            self._h, flat.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.POINTER(C.c_uint64)),
+            lens.ctypes.data_as(_u32p), len(lens), dim))
+        self.n, self.dim = len(lens), dim
+
+    def set_shard(self, rank, world):
+        self._check(self._lib.apd_set_shard(self._h, rank, world))
+
+    # -- the hot path ----------------------------------------------------------
+    def align_all(self, pct, ins=1.0, dele=1.0, mat=1.0, mode=APD_MODE_STRICT, out=None):
+        """Host-buffer call: n x n float32 (diag 0), host<->device copies included."""
+        n = self.n
+        if out is None:
+            out = np.empty((n, n), dtype=np.float32)
+        assert out.dtype == np.float32 and out.size == n * n and out.flags.c_contiguous
+        p = _c_params(pct, ins, dele, mat, mode)
+        self._check(self._lib.apd_align_all(self._h, C.byref(p), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def packed_len(self, pct, mode=APD_MODE_STRICT):
+        p = _c_params(pct, 1.0, 1.0, 1.0, mode)
+        v = C.c_uint64(0)
+        self._check(self._lib.apd_packed_len(self._h, C.byref(p), C.byref(v)))
+        return v.value
+
+    def align_packed(self, pct, ins, dele, mat, mode, d_packed_ptr, stream=0):
+        p = _c_params(pct, ins, dele, mat, mode)
+        self._check(self._lib.apd_align_packed(self._h, C.byref(p), C.c_void_p(d_packed_ptr),
+                                               C.c_void_p(stream)))
+
+    def scatter_packed(self, d_gathered_ptr, world, d_out_ptr, stream=0):
+        self._check(self._lib.apd_scatter_packed(self._h, C.c_void_p(d_gathered_ptr), world,
+                                                 C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
+    def synchronize(self, stream=0):
+        self._check(self._lib.apd_synchronize(self._h, C.c_void_p(stream)))
+
+    def align_pairs(self, pairs, pct=1.0, ins=1.0, dele=1.0, mat=1.0, mode=APD_MODE_STRICT,
+                    want_paths=False, path_cap=None, warping_band=None):
+        """Scores (and warping paths) of explicit ordered pairs [(i, j), ...]."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        k = len(pairs)
+        scores = np.empty(k, dtype=np.float32)
+        p = _c_params(pct, ins, dele, mat, mode)
+        paths = None
+        lens = np.zeros(max(k, 1), dtype=np.uint64)
+        paths_ptr = None
+        cap = 0
+        if want_paths:
+            cap = int(path_cap) if path_cap is not None else 0
+            paths = np.zeros((k, max(cap, 1), 2), dtype=np.uint32)
+            paths_ptr = paths.ctypes.data_as(_u32p)
+        args = [pairs.ctypes.data_as(_u32p), k, scores.ctypes.data_as(_fp), paths_ptr, cap,
+                lens.ctypes.data_as(C.POINTER(C.c_uint64))]
+        if warping_band is None:
+            st = self._lib.apd_align_pairs(self._h, C.byref(p), *args)
+        else:
+            st = self._lib.apd_align_pairs_band(self._h, C.byref(p), int(warping_band), *args)
+        self._check(st)
+        if not want_paths:
+            return scores
+        return scores, [paths[q, :min(int(lens[q]), cap)].copy() for q in range(k)], lens[:k].copy()
+
+    def stats(self):
+        s = apd_stats()
+        self._check(self._lib.apd_get_stats(self._h, C.byref(s)))
+        return {name: getattr(s, name) for name, _ in apd_stats._fields_}
+
+
+class _Mutex:
+    """Stand-in for Arc<Mutex<Vec<f32>>> (src/alignments.rs:13): `.lock().unwrap()`
+    yields the flat result vector, as at the call site src/main.rs:194-195."""
+
+    class _Guard:
+        def __init__(self, owner):
+            self._owner = owner
+
+        def unwrap(self):
+            return self._owner._value
+
+    def __init__(self, value):
+        self._value = value
+        self._lock = threading.Lock()
+
+    def lock(self):
+        return _Mutex._Guard(self)
+
+
+class AlignmentWorkers:
+    """Aligns all sequences and saves the results in a flat matrix (src/alignments.rs:11-68).
+
+    `alignment_workers` of the Discovery config is accepted and ignored: the work is
+    spread over the GPU by the library, not over host threads.
+    """
+
+    def __init__(self, data, device=0, mode=APD_MODE_STRICT):
+        self.data = list(data)
+        n = len(self.data)
+        self.result = _Mutex(np.zeros(n * n, dtype=np.float32))  # diag stays 0.0 (src/alignments.rs:20-23,51)
+        self.mode = mode
+        self._ctx = Context(device)
+        self._ctx.set_sequences(self.data)
+
+    @staticmethod
+    def new(data, device=0, mode=APD_MODE_STRICT):
+        return AlignmentWorkers(data, device, mode)
+
+    def align_all(self, params):
+        """params: a Discovery (src/discovery.rs:7-26).  Blocking; fills self.result."""
+        n = len(self.data)
+        if params.alignment_workers == 0:
+            # src/alignments.rs:33 divides by alignment_workers: the reference panics.
+            raise ZeroDivisionError("attempt to divide by zero (alignment_workers == 0)")
+        out = self.result.lock().unwrap()
+        self._ctx.align_all(params.warping_band_percentage, params.insertion_penalty,
+                            params.deletion_penalty, params.match_penalty, self.mode,
+                            out=out.reshape(n, n))
+
+    def stats(self):
+        return self._ctx.stats()
+
+
+class Alignment:
+    """One ordered pair (src/alignments.rs:99-181).  `sparse` is not materialised on the
+    host; `path` holds the device-traced warping path instead."""
+
+    def __init__(self, device=0, mode=APD_MODE_STRICT):
+        self.n = 0
+        self.m = 0
+        self._score = None
+        self.path = None
+        self._device = device
+        self._mode = mode
+
+    @staticmethod
+    def new(device=0, mode=APD_MODE_STRICT):
+        return Alignment(device, mode)
+
+    def construct_alignment(self, x, y, params, want_path=True):
+        xa = x.as_array() if isinstance(x, NDSequence) else np.ascontiguousarray(x, dtype=np.float32)
+        ya = y.as_array() if isinstance(y, NDSequence) else np.ascontiguousarray(y, dtype=np.float32)
+        if xa.ndim == 1:
+            xa = xa.reshape(-1, 1)
+        if ya.ndim == 1:
+            ya = ya.reshape(-1, 1)
+        self.n, self.m = xa.shape[0], ya.shape[0]
+        with Context(self._device) as ctx:
+            ctx.set_sequences([xa, ya], dim=xa.shape[1] if xa.shape[0] else ya.shape[1])
+            cap = self.n + self.m + 2
+            scores, paths, _ = ctx.align_pairs([(0, 1)], 0.0, params.insertion_penalty,
+                                               params.deletion_penalty, params.match_penalty,
+                                               self._mode, want_paths=True, path_cap=cap if want_path else 0,
+                                               warping_band=params.warping_band)
+        self._score = np.float32(scores[0])
+        self.path = paths[0] if want_path else None
+
+    def score(self):
+        """src/alignments.rs:116-125"""
+        if self._score is None:
+            return np.float32(np.inf)  # Alignment::new() has n == m == 0
+        return self._score

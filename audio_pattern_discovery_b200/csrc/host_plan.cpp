@@ -1,0 +1,179 @@
+// host_plan.cpp -- see host_plan.h.
+#include "host_plan.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "dtw_core.h"
+
+namespace apd {
+
+const int kSmemRingCaps[SMEM_RING_CAPS] = {16, 32, 56};
+
+std::string build_arena_layout(const uint32_t* lens, uint32_t n, uint32_t dim, Arena& out)
+{
+    if (dim == 0) return "dim must be >= 1";
+    if (n > 0 && !lens) return "null length table";
+    out = Arena();
+    out.n = n;
+    out.dim = dim;
+    out.dpad = (dim + 3u) & ~3u;
+    out.perm.resize(n);
+    std::iota(out.perm.begin(), out.perm.end(), 0u);
+    // Length-sorted ("length-bucketed") order: the 32 column sequences of a unit
+    // are neighbours in this order and therefore have similar band geometry.
+    std::stable_sort(out.perm.begin(), out.perm.end(),
+                     [&](uint32_t x, uint32_t y) { return lens[x] < lens[y]; });
+    out.len.resize(n);
+    out.off.resize(n);
+    uint64_t frames_total = 0;
+    for (uint32_t s = 0; s < n; s++) {
+        uint32_t src = out.perm[s];
+        if (lens[src] > (1u << 30)) return "sequence too long";
+        out.len[s] = lens[src];
+        frames_total += PRE_PAD_FRAMES;
+        if (frames_total + lens[src] >= (1ull << 32)) return "arena exceeds 2^32 frames";
+        out.off[s] = (uint32_t)frames_total;
+        frames_total += lens[src];
+    }
+    frames_total += PRE_PAD_FRAMES;  // slack behind the last sequence
+    out.total_frames = frames_total;
+    return "";
+}
+
+void fill_arena(const Arena& ar, const float* const* frames, float* dst)
+{
+    std::memset(dst, 0, (size_t)ar.total_frames * ar.dpad * sizeof(float));
+    for (uint32_t s = 0; s < ar.n; s++) {
+        const float* src = frames[ar.perm[s]];
+        float* d = dst + (size_t)ar.off[s] * ar.dpad;
+        if (!ar.len[s]) continue;
+        if (ar.dpad == ar.dim) {
+            std::memcpy(d, src, (size_t)ar.len[s] * ar.dim * sizeof(float));
+        } else {
+            for (uint32_t t = 0; t < ar.len[s]; t++)
+                std::memcpy(d + (size_t)t * ar.dpad, src + (size_t)t * ar.dim, ar.dim * sizeof(float));
+        }
+    }
+}
+
+std::string build_arena(const float* const* frames, const uint32_t* lens, uint32_t n,
+                        uint32_t dim, Arena& out)
+{
+    std::string err = build_arena_layout(lens, n, dim, out);
+    if (!err.empty()) return err;
+    for (uint32_t s = 0; s < n; s++)
+        if (lens[s] > 0 && (!frames || !frames[s])) return "null frames pointer for a non-empty sequence";
+    out.data.resize((size_t)out.total_frames * out.dpad);
+    fill_arena(out, frames, out.data.data());
+    return "";
+}
+
+void build_unit_plan(const Arena& ar, float pct, UnitPlan& out)
+{
+    out = UnitPlan();
+    out.pct = pct;
+    const uint32_t N = ar.n;
+    if (N < 2) return;
+    const uint32_t nblocks = (N + 31) / 32;
+
+    struct Tmp { Unit u; uint32_t cost; int cls; int need; };
+    std::vector<Tmp> tmp;
+    tmp.reserve((size_t)N * (nblocks / 2 + 1));
+    const int n_cls = SMEM_RING_CAPS + 1;
+    int cls_need[SMEM_RING_CAPS + 1] = {0, 0, 0, 0};
+    uint64_t cls_count[SMEM_RING_CAPS + 1] = {0, 0, 0, 0};
+    uint32_t max_cost = 1;
+    for (uint32_t a = 0; a + 1 < N; a++) {
+        const int n = (int)ar.len[a];
+        for (uint32_t B = (a + 1) / 32; B < nblocks; B++) {
+            uint32_t last = std::min(32 * B + 31, N - 1);
+            const int mmax = (int)ar.len[last];  // sorted ascending: the block's longest
+            // b > a in sorted order => m >= n, and window_of is monotone in m there.
+            const int wmax = window_of(pct, n, mmax);
+            const int It = (n + 3) >> 2, Jt = (mmax + 3) >> 2;
+            const int need = ring_tiles_needed(wmax, It > 0 ? It : 1);
+            int span = need - 1;
+            uint64_t cost64 = (uint64_t)std::max(Jt, 1) * (uint64_t)std::max(span, 1);
+            uint32_t cost = (uint32_t)std::min<uint64_t>(cost64, 0xffffffffu);
+            int cls = SMEM_RING_CAPS;  // gstate
+            for (int k = 0; k < SMEM_RING_CAPS; k++)
+                if (need <= kSmemRingCaps[k]) { cls = k; break; }
+            cls_need[cls] = std::max(cls_need[cls], need);
+            cls_count[cls]++;
+            max_cost = std::max(max_cost, cost);
+            out.tiles_estimate += cost;
+            Tmp t;
+            t.u.a = a; t.u.B = B; t.cost = cost; t.cls = cls; t.need = need;
+            tmp.push_back(t);
+        }
+    }
+    // Bucket sort inside each class, expensive first (LPT order for the dynamic
+    // unit fetch; exact order is irrelevant).
+    const int NB = 1024;
+    std::vector<uint64_t> start((size_t)n_cls * NB + 1, 0);
+    auto bucket = [&](const Tmp& t) {
+        uint64_t q = (uint64_t)t.cost * (NB - 1) / max_cost;  // 0..NB-1, monotone in cost
+        return (size_t)t.cls * NB + (size_t)(NB - 1 - q);
+    };
+    for (const Tmp& t : tmp) start[bucket(t) + 1]++;
+    for (size_t k = 1; k < start.size(); k++) start[k] += start[k - 1];
+    out.units.resize(tmp.size());
+    std::vector<uint64_t> cursor(start.begin(), start.end() - 1);
+    for (const Tmp& t : tmp) out.units[cursor[bucket(t)]++] = t.u;
+    uint64_t pos = 0;
+    for (int c = 0; c < n_cls; c++) {
+        if (!cls_count[c]) continue;
+        UnitClass uc;
+        uc.begin = pos;
+        uc.end = pos + cls_count[c];
+        uc.St = cls_need[c];
+        uc.gstate = (c == SMEM_RING_CAPS);
+        out.classes.push_back(uc);
+        pos = uc.end;
+    }
+}
+
+// sum_{k=0}^{K-1} max(0, min(A, B-k))
+static uint64_t band_sum(int64_t A, int64_t B, int64_t K)
+{
+    if (A <= 0 || B <= 0 || K <= 0) return 0;
+    int64_t k1 = std::min<int64_t>(std::max<int64_t>(B - A + 1, 0), K);  // terms equal to A
+    int64_t k2 = std::min<int64_t>(B, K);                                // positive terms
+    uint64_t s = (uint64_t)(A * k1);
+    if (k2 > k1) s += (uint64_t)((k2 - k1) * B - (k1 + k2 - 1) * (k2 - k1) / 2);
+    return s;
+}
+
+uint64_t cells_visited(uint64_t n, uint64_t m, uint64_t w)
+{
+    // diagonals j-i = 0..w-1 hold min(n, m-k) cells, diagonals j-i = -1..-w hold min(m, n-k)
+    return band_sum((int64_t)n, (int64_t)m, (int64_t)w) +
+           band_sum((int64_t)m, (int64_t)n - 1, (int64_t)w);
+}
+
+uint64_t reference_cells(const Arena& ar, const UnitPlan& plan, uint32_t rank, uint32_t world)
+{
+    uint64_t total = 0;
+    const uint32_t N = ar.n;
+    for (uint64_t u = rank; u < plan.units.size(); u += world) {
+        const Unit& un = plan.units[u];
+        const uint64_t n = ar.len[un.a];
+        uint32_t b = std::max(32 * un.B, un.a + 1);
+        const uint32_t bend = std::min(32 * un.B + 32, N);
+        while (b < bend) {  // runs of equal length share one closed-form evaluation
+            uint32_t e = b + 1;
+            while (e < bend && ar.len[e] == ar.len[b]) e++;
+            const uint64_t m = ar.len[b];
+            if (n >= 1 && m >= 1) {
+                uint64_t w = (uint64_t)window_of(plan.pct, (int)n, (int)m);
+                total += (uint64_t)(e - b) * (cells_visited(n, m, w) + cells_visited(m, n, w));
+            }
+            b = e;
+        }
+    }
+    return total;
+}
+
+}  // namespace apd

@@ -1,0 +1,76 @@
+"""One process per GPU: shard the work units of the all-pairs matrix over the ranks of a
+torch.distributed process group and assemble the full matrix on every rank with ONE
+all-gather of the packed per-shard results (NCCL over NVLink/NVSwitch), followed by the
+library's scatter kernel.  Pairs are independent, so the all-gather is the only
+collective on the path.
+
+torch is used for device buffers, streams and the process group only.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .alignments import APD_MODE_STRICT, Context
+
+
+class ShardedAligner:
+    def __init__(self, seqs, device=None, group=None, mode=APD_MODE_STRICT):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device)
+        self.mode = mode
+        self.ctx = Context(device)
+        self.ctx.set_sequences(seqs)       # every rank holds the whole arena (<= ~0.4 GB)
+        self.ctx.set_shard(self.rank, self.world)
+        self.n = self.ctx.n
+        self._packed = None
+        self._gathered = None
+        self._matrix = None
+
+    def set_sequences(self, seqs):
+        self.ctx.set_sequences(seqs)
+        self.n = self.ctx.n
+
+    def align_all_device(self, pct, ins=1.0, dele=1.0, mat=1.0):
+        """-> (n, n) float32 CUDA tensor holding the full matrix on this rank."""
+        k = self.ctx.packed_len(pct, self.mode)
+        if self._packed is None or self._packed.numel() != k:
+            self._packed = torch.empty(k, dtype=torch.float32, device=self.device)
+            self._gathered = (torch.empty(k * self.world, dtype=torch.float32, device=self.device)
+                              if self.world > 1 else self._packed)
+        if self._matrix is None or self._matrix.shape[0] != self.n:
+            self._matrix = torch.empty((self.n, self.n), dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device)
+        self.ctx.align_packed(pct, ins, dele, mat, self.mode, self._packed.data_ptr(), stream.cuda_stream)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self._gathered, self._packed, group=self.group)
+        self.ctx.scatter_packed(self._gathered.data_ptr(), self.world, self._matrix.data_ptr(),
+                                stream.cuda_stream)
+        return self._matrix
+
+    def align_all(self, pct, ins=1.0, dele=1.0, mat=1.0, out=None, to_host=True):
+        """Full matrix as a host array on the ranks that ask for it (to_host)."""
+        m = self.align_all_device(pct, ins, dele, mat)
+        stream = torch.cuda.current_stream(self.device)
+        res = None
+        if to_host:
+            if out is None:
+                out = torch.empty((self.n, self.n), dtype=torch.float32, pin_memory=True)
+            out.copy_(m, non_blocking=True)
+            res = out
+        self.ctx.synchronize(stream.cuda_stream)
+        return res
+
+    def stats(self):
+        return self.ctx.stats()
+
+    def close(self):
+        self.ctx.close()
+
+
+def partition_check(n_units, world):
+    """Units u with u % world == rank: sizes per rank (host-side helper for tests)."""
+    return [len(range(r, n_units, world)) for r in range(world)]

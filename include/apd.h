@@ -1,0 +1,158 @@
+/*
+ * apd.h -- C ABI of libapd_b200: the B200-native replacement for the all-pairs
+ * weighted, Sakoe-Chiba-banded DTW distance matrix of
+ * dkohlsdorf/audio_pattern_discovery (the path SURVEY.md section 8 scopes).
+ *
+ * This is the boundary a Rust `apd-sys` crate binds with `extern "C"` (see
+ * INTEGRATION.md and rust/); every entry point names the reference interface it
+ * replaces (file:line relative to the reference repository root).
+ *
+ * Conventions: plain pointers and sizes only; every function returns an
+ * apd_status (0 = OK) and never unwinds; a context is thread-compatible (one
+ * caller at a time); the library copies inputs before returning and writes only
+ * into caller-allocated outputs.  There is NO CPU fallback: without a CUDA
+ * device apd_create() fails with APD_ERR_NO_DEVICE.
+ */
+#ifndef APD_H
+#define APD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APD_ABI_VERSION 1
+
+typedef enum {
+    APD_OK = 0,
+    APD_ERR_INVALID = 1,     /* bad argument (message in apd_last_error) */
+    APD_ERR_NO_DEVICE = 2,   /* no usable CUDA device: this library has no CPU path */
+    APD_ERR_CUDA = 3,        /* a CUDA runtime call failed */
+    APD_ERR_UNSUPPORTED = 4, /* e.g. dim > APD_MAX_DIM */
+    APD_ERR_STATE = 5,       /* call order (no sequences set, ...) */
+    APD_ERR_INTERNAL = 6
+} apd_status;
+
+#define APD_MAX_DIM 32
+
+/* Arithmetic variants of the distance kernel. */
+#define APD_MODE_STRICT 0u /* bit-exact with the reference's f32 operation sequence (default) */
+#define APD_MODE_FAST 1u   /* packed-FMA accumulation + approximate sqrt; <= 1e-5 relative */
+
+typedef struct apd_ctx apd_ctx;
+
+/* Replaces src/discovery.rs:38-45 (Discovery::alignment_params) + src/alignments.rs:77-83
+ * (AlignmentParams).  The per-pair band is derived on the device exactly as the
+ * reference does: band = (warping_band_percentage * max(len_i, len_j) as f32) as usize. */
+typedef struct {
+    float warping_band_percentage; /* project/config/Discovery.toml:17 */
+    float insertion_penalty;       /* :18  weight on predecessor (i-1, j)   */
+    float deletion_penalty;        /* :19  weight on predecessor (i, j-1)   */
+    float match_penalty;           /* :20  weight on predecessor (i-1, j-1) */
+    uint32_t mode;                 /* APD_MODE_* */
+} apd_params;
+
+typedef struct {
+    uint64_t n_sequences;
+    uint64_t ordered_pairs;      /* n(n-1): what src/alignments.rs:50-51 enumerates */
+    uint64_t units_total;        /* 32-pair work units over the whole matrix */
+    uint64_t units_local;        /* ... handled by this context's shard */
+    uint64_t cells_reference;    /* reference cell updates of this shard's ordered pairs
+                                    (src/alignments.rs:174-175 visit rule) */
+    uint64_t cells_computed;     /* cell updates the kernels actually execute (both orientations) */
+    uint32_t kernel_launches;    /* DTW + scatter launches of the last align call */
+    float kernel_ms;             /* CUDA-event time of the DTW kernels of the last call */
+    float scatter_ms;            /* packed -> n x n scatter kernel */
+    float h2d_ms, d2h_ms;        /* host<->device copies inside the last host-buffer call */
+    uint64_t h2d_bytes, d2h_bytes;
+    float sm_clock_mhz;          /* clock rate the device reports (max), for rooflines */
+    uint32_t sm_count;
+} apd_stats;
+
+/* ---- lifecycle ------------------------------------------------------------ */
+
+/* One context drives one CUDA device.  Replaces AlignmentWorkers::new's role of
+ * owning the data (src/alignments.rs:17-26). */
+apd_status apd_create(int device_id, apd_ctx **out);
+void apd_destroy(apd_ctx *ctx);
+const char *apd_last_error(const apd_ctx *ctx); /* ctx may be NULL: last create error */
+uint32_t apd_abi_version(void);
+
+/* ---- sequence packing (the spectrogram.rs / discovery.rs glue) ------------- */
+
+/* Replaces the Vec<NDSequence> hand-over of src/main.rs:189 and the NDSequence
+ * layout contract (src/spectrogram.rs:13-24, vec() 99-101, len() 152-154):
+ * frames[s] points at lens[s] * dim row-major f32 values.  Sequences are copied,
+ * sorted by length and packed into one 16-byte-aligned device arena. */
+apd_status apd_set_sequences(apd_ctx *ctx, const float *const *frames, const uint32_t *lens,
+                             uint32_t n, uint32_t dim);
+
+/* Same, from one flat buffer: sequence s starts at flat + offsets[s] (in floats). */
+apd_status apd_set_sequences_flat(apd_ctx *ctx, const float *flat, const uint64_t *offsets,
+                                  const uint32_t *lens, uint32_t n, uint32_t dim);
+
+/* Multi-process sharding (one process per GPU, e.g. under torchrun): this
+ * context computes work units u with u % world == rank.  Default 0 / 1. */
+apd_status apd_set_shard(apd_ctx *ctx, uint32_t rank, uint32_t world);
+
+/* ---- the hot path ---------------------------------------------------------- */
+
+/* Replaces AlignmentWorkers::align_all + the result hand-over
+ * (src/alignments.rs:31-67, src/main.rs:191-195): fills out_nxn (host memory,
+ * n*n floats, row-major, result[i*n+j] = score(data[i], data[j]), diagonal 0.0).
+ * With world > 1 only this shard's pairs are non-zero; use the device-side calls
+ * below plus an all-gather to assemble the full matrix. */
+apd_status apd_align_all(apd_ctx *ctx, const apd_params *p, float *out_nxn);
+
+/* Device-resident stages of the same call, for callers that own device buffers
+ * (PyTorch tensors, NCCL):
+ *   1. apd_packed_len: floats in one shard's packed result buffer (identical on
+ *      every rank so that the buffers can be all-gathered; depends on p only
+ *      through warping_band_percentage);
+ *   2. apd_align_packed: run the DTW kernels of this shard, results ->
+ *      d_packed (device pointer, apd_packed_len floats);
+ *   3. apd_scatter_packed: expand `world` gathered shards (device pointer,
+ *      world * apd_packed_len floats, rank-major; world == 1 on a sharded context
+ *      means "this shard's buffer only") into the device matrix d_out_nxn (n*n
+ *      floats, diagonal 0).
+ * All work is enqueued on `stream` (a cudaStream_t, 0 = default stream). */
+apd_status apd_packed_len(apd_ctx *ctx, const apd_params *p, uint64_t *n_floats);
+apd_status apd_align_packed(apd_ctx *ctx, const apd_params *p, float *d_packed, void *stream);
+apd_status apd_scatter_packed(apd_ctx *ctx, const float *d_gathered, uint32_t world,
+                              float *d_out_nxn, void *stream);
+/* Waits for `stream` (0 = the context's own), collects kernel timings and checks the
+ * device-side error flag of the preceding apd_align_packed. */
+apd_status apd_synchronize(apd_ctx *ctx, void *stream);
+
+/* Replaces Alignment::new + construct_alignment + score for one ordered pair
+ * (src/alignments.rs:106-125,165-180), with the warping path traced on the
+ * device (the reference keeps `sparse` for this but never walks it; the path
+ * definition is SURVEY.md Appendix A.8).  path_ij receives up to path_cap
+ * (i, j) pairs, 1-based, end-to-start; *path_len the full length.  path_ij may
+ * be NULL. */
+apd_status apd_align_pair(apd_ctx *ctx, const apd_params *p, uint32_t i, uint32_t j,
+                          float *score, uint32_t *path_ij, uint64_t path_cap,
+                          uint64_t *path_len);
+
+/* Batch form: pairs_ij = n_pairs ordered (i, j) pairs; scores[k]; pair k's path at
+ * paths_ij + k * path_cap * 2 (may be NULL); path_lens[k] (may be NULL). */
+apd_status apd_align_pairs(apd_ctx *ctx, const apd_params *p, const uint32_t *pairs_ij,
+                           uint64_t n_pairs, float *scores, uint32_t *paths_ij,
+                           uint64_t path_cap, uint64_t *path_lens);
+
+/* Same with the caller's own AlignmentParams.warping_band (src/alignments.rs:79) in
+ * place of the percentage-derived one: what Alignment::construct_alignment receives
+ * when it is called outside align_all (p->warping_band_percentage is ignored). */
+apd_status apd_align_pairs_band(apd_ctx *ctx, const apd_params *p, uint64_t warping_band,
+                                const uint32_t *pairs_ij, uint64_t n_pairs, float *scores,
+                                uint32_t *paths_ij, uint64_t path_cap, uint64_t *path_lens);
+
+/* ---- introspection --------------------------------------------------------- */
+apd_status apd_get_stats(apd_ctx *ctx, apd_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APD_H */

@@ -1,0 +1,172 @@
+// dtw_emul.cpp -- host-side emulator of the CUDA kernel's schedule (TEST ONLY).
+//
+// Compiles audio_pattern_discovery_b200/csrc/dtw_core.h (the per-lane program the
+// kernels run) and host_plan.cpp (arena packing + unit planning) with g++ and runs
+// every lane of every work unit sequentially, with the warp reductions replaced by
+// loops over the 32 lanes' geometry.  It lets the CPU test-suite check tiling, band
+// masks, the boundary ring and the planner against the oracle without a GPU.  It is
+// NOT a fallback: nothing in the package loads it.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../audio_pattern_discovery_b200/csrc/dtw_core.h"
+#include "../../audio_pattern_discovery_b200/csrc/host_plan.h"
+
+using namespace apd;
+
+namespace {
+
+template <int DPAD>
+struct HostCtx {
+    const LaneGeom* lanes;  // 32
+    RowGeom rg;
+    int lane;
+    const float* xbase;  // frame 0 of x
+    const float* ybase;  // frame 0 of this lane's y
+    std::vector<F2> state;
+    const float* cur;
+    const float* nxt;
+    uint64_t tiles = 0;
+
+    void row_range(int J, int& Ilo, int& Ihi) const
+    {
+        Ilo = 0x3fffffff; Ihi = -1;
+        for (int l = 0; l < 32; l++) {
+            int lo, hi;
+            lane_row_range(lanes[l], rg, J, lo, hi);
+            if (lo < Ilo) Ilo = lo;
+            if (hi > Ihi) Ihi = hi;
+        }
+    }
+    bool interior(int I, int J) const
+    {
+        for (int l = 0; l < 32; l++)
+            if (!lane_tile_interior(lanes[l], rg, I, J)) return false;
+        return true;
+    }
+    const float* xaddr(int I) const { return xbase + (int64_t)(4 * I - rg.rho - 1) * DPAD; }
+    void x_preload(int I) { cur = xaddr(I); }
+    void x_prefetch(int I) { nxt = xaddr(I); tiles++; }
+    const float* x_tile() const { return cur; }
+    void x_commit() { cur = nxt; }
+    F2 st_load(int row) const { return state[row]; }
+    void st_store(int row, F2 v) { state[row] = v; }
+    void load_y(int J, F2 (&yv)[TILE][DPAD / 2]) const
+    {
+        const float* p = ybase + (int64_t)(4 * J - lanes[lane].gamma - 1) * DPAD;
+        for (int c = 0; c < TILE; c++)
+            for (int k = 0; k < DPAD / 2; k++) yv[c][k] = mk2(p[c * DPAD + 2 * k], p[c * DPAD + 2 * k + 1]);
+    }
+};
+
+template <int DPAD>
+int run_all(const Arena& ar, const UnitPlan& plan, float pct, Penalties pen, bool strict,
+            bool unitw, uint32_t rank, uint32_t world, float* out, uint64_t* tiles_out)
+{
+    const uint32_t N = ar.n;
+    uint64_t tiles = 0;
+    for (const UnitClass& uc : plan.classes) {
+        for (uint64_t u = uc.begin; u < uc.end; u++) {
+            if (u % world != rank) continue;
+            const Unit un = plan.units[u];
+            const int n = (int)ar.len[un.a];
+            RowGeom rg = row_geometry(n);
+            LaneGeom lanes[32];
+            int Jt_max = 0, wmax = 0;
+            for (int l = 0; l < 32; l++) {
+                uint32_t b = 32 * un.B + l;
+                bool exists = b > un.a && b < N;
+                lanes[l] = lane_geometry(exists, n, exists ? (int)ar.len[b] : 0, pct);
+                if (lanes[l].Jt > Jt_max) Jt_max = lanes[l].Jt;
+                if (lanes[l].active && lanes[l].w > wmax) wmax = lanes[l].w;
+            }
+            if (ring_tiles_needed(wmax, rg.It > 0 ? rg.It : 1) > uc.St) return -10;  // planner bug
+            for (int l = 0; l < 32; l++) {
+                uint32_t b = 32 * un.B + l;
+                if (!(b > un.a && b < N)) continue;
+                const int m = (int)ar.len[b];
+                float s1, s2;
+                if (!lanes[l].active) {
+                    s1 = s2 = INFINITY;  // src/alignments.rs:116-125 with an empty side
+                } else {
+                    HostCtx<DPAD> ctx;
+                    ctx.lanes = lanes; ctx.rg = rg; ctx.lane = l;
+                    ctx.xbase = ar.data.data() + (size_t)ar.off[un.a] * DPAD;
+                    ctx.ybase = ar.data.data() + (size_t)ar.off[b] * DPAD;
+                    F2 poison = mk2(-12345.0f, -54321.0f);  // stale ring entries must never be read
+                    ctx.state.assign((size_t)uc.St * TILE, poison);
+                    ctx.cur = ctx.nxt = nullptr;
+                    F2 acc;
+                    if (strict && unitw) acc = run_unit<DPAD, true, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen);
+                    else if (strict) acc = run_unit<DPAD, true, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen);
+                    else if (unitw) acc = run_unit<DPAD, false, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen);
+                    else acc = run_unit<DPAD, false, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen);
+                    s1 = finish_score(acc.x, n, m);
+                    s2 = finish_score(acc.y, n, m);
+                    if (l == 0 || tiles == 0) tiles += 0;
+                    tiles += ctx.tiles;
+                }
+                const uint32_t ia = ar.perm[un.a], ib = ar.perm[b];
+                out[(size_t)ia * N + ib] = s1;
+                out[(size_t)ib * N + ia] = s2;
+            }
+        }
+    }
+    if (tiles_out) *tiles_out = tiles;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Emulates apd_align_all (include/apd.h) for shard (rank, world) on the host.
+// info (may be NULL) receives: [0] units, [1] classes, [2] reference cells of the
+// shard, [3] lane-tiles executed, [4..7] St of up to four classes, [8..11] 1 if gstate.
+int apd_emul_align_all(const float* const* frames, const uint32_t* lens, uint32_t n, uint32_t dim,
+                       float pct, float ins, float del, float mat, int strict, uint32_t rank,
+                       uint32_t world, float* out_nxn, uint64_t* info)
+{
+    Arena ar;
+    std::string err = build_arena(frames, lens, n, dim, ar);
+    if (!err.empty()) return -1;
+    if (ar.dpad > 32) return -2;
+    UnitPlan plan;
+    build_unit_plan(ar, pct, plan);
+    std::memset(out_nxn, 0, (size_t)n * n * sizeof(float));
+    Penalties pen; pen.ins = ins; pen.del = del; pen.mat = mat;
+    const bool unitw = (ins == 1.0f && del == 1.0f && mat == 1.0f);
+    uint64_t tiles = 0;
+    int rc;
+    switch (ar.dpad) {
+        case 4: rc = run_all<4>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 8: rc = run_all<8>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 12: rc = run_all<12>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 16: rc = run_all<16>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 20: rc = run_all<20>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 24: rc = run_all<24>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 28: rc = run_all<28>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 32: rc = run_all<32>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        default: return -3;
+    }
+    if (info) {
+        std::memset(info, 0, 12 * sizeof(uint64_t));
+        info[0] = plan.units.size();
+        info[1] = plan.classes.size();
+        info[2] = reference_cells(ar, plan, rank, world);
+        info[3] = tiles;
+        for (size_t c = 0; c < plan.classes.size() && c < 4; c++) {
+            info[4 + c] = (uint64_t)plan.classes[c].St;
+            info[8 + c] = plan.classes[c].gstate ? 1 : 0;
+        }
+    }
+    return rc;
+}
+
+uint64_t apd_emul_cells_visited(uint64_t n, uint64_t m, uint64_t w) { return cells_visited(n, m, w); }
+
+int apd_emul_window(float pct, int n, int m) { return window_of(pct, n, m); }
+
+}  // extern "C"

@@ -1,0 +1,100 @@
+"""Runs the kernel's per-lane program (csrc/dtw_core.h) and the host planner
+(csrc/host_plan.cpp) through the host-side schedule emulator and compares the
+full matrix with the oracle bit for bit.  No GPU involved; the emulator is test
+code, not a fallback (nothing in the package loads it)."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+from . import emul
+from .conftest import random_sequences
+
+
+def bits(a):
+    return np.asarray(a, dtype=np.float32).view(np.uint32)
+
+
+CASES = [
+    # (n_seq, len_lo, len_hi, dim, pct, (ins, del, mat), integer)
+    (9, 1, 12, 1, 0.0, (1.0, 1.0, 1.0), True),
+    (12, 1, 30, 3, 0.1, (1.0, 1.0, 1.0), True),
+    (12, 2, 40, 2, 0.25, (0.75, 0.5, 1.0), True),
+    (40, 5, 60, 8, 0.1, (1.0, 1.0, 1.0), False),
+    (35, 20, 90, 10, 0.05, (0.75, 0.5, 1.0), False),
+    (20, 30, 70, 20, 1.0, (1.0, 1.0, 1.0), False),
+    (10, 50, 130, 26, 0.1, (0.5, 1.0, 0.25), False),
+    (70, 1, 20, 4, 0.3, (1.0, 1.0, 1.0), True),   # more than two 32-lane blocks
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_emulated_schedule_matches_oracle_bitwise(case):
+    n, lo, hi, dim, pct, (ins, dele, mat), integer = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    seqs = random_sequences(rng, n, lo, hi, dim, integer)
+    want = oracle.align_all(seqs, pct, ins, dele, mat, workers=4, variant="dense")
+    got, info = emul.align_all(seqs, pct, ins, dele, mat, strict=True)
+    assert np.array_equal(bits(got), bits(want))
+    ref_cells = sum(oracle.pair_cells(len(a), len(b), pct)
+                    for i, a in enumerate(seqs) for j, b in enumerate(seqs) if i != j and len(a) and len(b))
+    assert int(info[2]) == ref_cells
+
+
+def test_fast_mode_within_tolerance():
+    rng = np.random.default_rng(3)
+    seqs = random_sequences(rng, 20, 30, 80, 20, False)
+    want = oracle.align_all(seqs, 0.1, 0.75, 0.5, 1.0, variant="dense")
+    got, _ = emul.align_all(seqs, 0.1, 0.75, 0.5, 1.0, strict=False)
+    off = ~np.eye(len(seqs), dtype=bool)
+    rel = np.abs(got[off] - want[off]) / np.abs(want[off])
+    assert rel.max() <= 1e-5  # BASELINE.json north_star tolerance
+
+
+def test_empty_and_single_frame_sequences():
+    rng = np.random.default_rng(4)
+    seqs = random_sequences(rng, 6, 3, 9, 2, True)
+    seqs[1] = np.zeros((0, 2), dtype=np.float32)
+    seqs[3] = np.ones((1, 2), dtype=np.float32)
+    seqs[4] = np.ones((1, 2), dtype=np.float32) * 2
+    want = oracle.align_all(seqs, 0.5, variant="literal")
+    got, _ = emul.align_all(seqs, 0.5)
+    assert np.array_equal(bits(got), bits(want))
+    assert np.isinf(got[1, 0]) and got[3, 4] == 0.0 and np.isinf(got[3, 0])
+
+
+def test_wide_band_uses_global_ring_class():
+    rng = np.random.default_rng(5)
+    seqs = random_sequences(rng, 5, 250, 300, 4, False)
+    got, info = emul.align_all(seqs, 1.0)
+    want = oracle.align_all(seqs, 1.0, variant="dense")
+    assert np.array_equal(bits(got), bits(want))
+    assert any(int(info[8 + c]) == 1 for c in range(int(info[1])))  # a gstate class exists
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_shards_partition_the_matrix(world):
+    rng = np.random.default_rng(6)
+    seqs = random_sequences(rng, 45, 4, 25, 3, True)
+    full, info = emul.align_all(seqs, 0.2)
+    acc = np.zeros_like(full)
+    seen = np.zeros(full.shape, dtype=np.int32)
+    cells = 0
+    for r in range(world):
+        part, pinfo = emul.align_all(seqs, 0.2, rank=r, world=world)
+        seen += (part != 0)
+        acc += part
+        cells += int(pinfo[2])
+    assert np.array_equal(bits(acc), bits(full))
+    assert seen.max() <= 1
+    assert cells == int(info[2])
+
+
+def test_cells_visited_closed_form():
+    L = emul.lib()
+    for n, m, w in [(512, 512, 53), (4096, 4096, 4098), (64, 256, 194), (128, 1024, 898), (1, 1, 2),
+                    (5, 9, 6), (9, 5, 6), (7, 7, 2), (3, 20, 19), (20, 3, 19), (2, 1, 3)]:
+        assert L.apd_emul_cells_visited(n, m, w) == oracle.cells_visited(n, m, w)
+    for pct, n, m in [(0.1, 512, 512), (0.05, 1024, 128), (1.0, 4096, 4096), (0.0, 9, 4), (float("nan"), 5, 5)]:
+        want = oracle.window(oracle.warping_band(pct, max(n, m)), n, m)
+        assert L.apd_emul_window(pct, n, m) == min(want, n + m + 8)
