@@ -22,6 +22,9 @@ class ShardedAligner:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device)
         self.mode = mode
+        # A real (non-default) stream: the library treats stream 0 as "the context's own
+        # stream", and torch events only see the stream they are recorded on.
+        self.stream = torch.cuda.Stream(self.device)
         self.ctx = Context(device)
         self.ctx.set_sequences(seqs)       # every rank holds the whole arena (<= ~0.4 GB)
         self.ctx.set_shard(self.rank, self.world)
@@ -43,26 +46,31 @@ class ShardedAligner:
                               if self.world > 1 else self._packed)
         if self._matrix is None or self._matrix.shape[0] != self.n:
             self._matrix = torch.empty((self.n, self.n), dtype=torch.float32, device=self.device)
-        stream = torch.cuda.current_stream(self.device)
-        self.ctx.align_packed(pct, ins, dele, mat, self.mode, self._packed.data_ptr(), stream.cuda_stream)
-        if self.world > 1:
-            dist.all_gather_into_tensor(self._gathered, self._packed, group=self.group)
-        self.ctx.scatter_packed(self._gathered.data_ptr(), self.world, self._matrix.data_ptr(),
-                                stream.cuda_stream)
+        stream = self.stream
+        with torch.cuda.stream(stream):
+            self.ctx.align_packed(pct, ins, dele, mat, self.mode, self._packed.data_ptr(), stream.cuda_stream)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self._gathered, self._packed, group=self.group)
+            self.ctx.scatter_packed(self._gathered.data_ptr(), self.world, self._matrix.data_ptr(),
+                                    stream.cuda_stream)
         return self._matrix
 
     def align_all(self, pct, ins=1.0, dele=1.0, mat=1.0, out=None, to_host=True):
         """Full matrix as a host array on the ranks that ask for it (to_host)."""
         m = self.align_all_device(pct, ins, dele, mat)
-        stream = torch.cuda.current_stream(self.device)
+        stream = self.stream
         res = None
         if to_host:
             if out is None:
                 out = torch.empty((self.n, self.n), dtype=torch.float32, pin_memory=True)
-            out.copy_(m, non_blocking=True)
+            with torch.cuda.stream(stream):
+                out.copy_(m, non_blocking=True)
             res = out
         self.ctx.synchronize(stream.cuda_stream)
         return res
+
+    def synchronize(self):
+        self.ctx.synchronize(self.stream.cuda_stream)
 
     def stats(self):
         return self.ctx.stats()

@@ -245,7 +245,7 @@ def run_b200(args):
     # ---- device-resident arm ----------------------------------------------------
     for _ in range(args.warmup):
         al.align_all_device(c["pct"], ins, dele, mat)
-        al.ctx.synchronize(torch.cuda.current_stream().cuda_stream)
+        al.synchronize()
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -255,11 +255,12 @@ def run_b200(args):
     for _ in range(args.steps):
         if flush is not None:
             flush.fill_(1.0)
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(al.stream)                         # events on the stream the kernels are launched on
         al.align_all_device(c["pct"], ins, dele, mat)
-        e1.record()
-        al.ctx.synchronize(torch.cuda.current_stream().cuda_stream)
+        e1.record(al.stream)
+        al.synchronize()
         torch.cuda.synchronize()
         step_ms.append(e0.elapsed_time(e1))
         st = al.stats()
@@ -282,11 +283,10 @@ def run_b200(args):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        e0.record()
+        e0.record(al.stream)
         al.set_sequences(seqs)                       # host packing + H2D of the arena
-        al.ctx.set_shard(rank, world)
         al.align_all(c["pct"], ins, dele, mat, out=host_out, to_host=(rank == 0))
-        e1.record()
+        e1.record(al.stream)
         torch.cuda.synchronize()
         dt = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
         if it >= 1:
