@@ -7,11 +7,12 @@
 //
 // Data layout (see host_plan.h): one arena of zero-padded DPAD-float frames, every
 // frame 16-byte aligned, sequences sorted by length.  Per warp in shared memory:
-//   xs   : 2 x (4 frames x DPAD floats)  double-buffered stage of the shared row
-//          sequence x (coalesced LDG.128 by lanes < DPAD -> STS.128, read back as
-//          warp-broadcast LDS.128)
-//   ring : St tiles x 4 rows x 32 lanes x float2 -- boundary column of the previous
-//          column block, lane-contiguous so LDS.64/STS.64 are conflict-free.
+//   xs   : 3 x (4 frames x DPAD floats)  stage of the shared row sequence x, two tiles
+//          ahead of the recurrence (coalesced LDG.128 by lanes < DPAD -> STS.128, read
+//          back as warp-broadcast LDS.128)
+//   ring : St tiles x 2 halves x 32 lanes x float4 -- boundary column of the previous
+//          column block ((D1, D2) of 2 rows per float4), lane-contiguous so LDS.128 /
+//          STS.128 are conflict-free.
 // GSTATE kernels keep the ring in a per-CTA slice of a global scratch buffer
 // instead (same layout, coalesced 256-byte rows, L2 resident) for bands too wide
 // for shared memory.
@@ -45,6 +46,8 @@ struct KernelArgs {
 
 #if defined(__CUDACC__)
 
+enum { X_STAGES = 3 };  // x row-tile stage buffers per warp
+
 template <int DPAD>
 struct DevCtx {
     LaneGeom lg;
@@ -52,59 +55,82 @@ struct DevCtx {
     int lane;
     const float4* xbase4;  // frame 0 of x
     const float4* ybase4;  // frame 0 of this lane's y
-    float4* xs4;           // 2 x DPAD float4
-    F2* st;                // this lane's ring column; row r lives at st[r * 32]
-    int cur;
+    float4* xs4;           // X_STAGES x DPAD float4
+    float4* ring4;         // this lane's ring column: tile s, half h at ring4[(2 * s + h) * 32]
     float4 xreg;
     unsigned int tiles;
 
-    APD_D void row_range(int J, int& Ilo, int& Ihi) const
+    APD_D void sweep_info(int J, int& Ilo, int& Ihi, int& Nlo, int& Nhi) const
     {
-        int lo, hi;
+        int lo, hi, nlo, nhi;
         lane_row_range(lg, rg, J, lo, hi);
+        lane_interior_range(lg, rg, J, nlo, nhi);
         Ilo = __reduce_min_sync(0xffffffffu, lo);
         Ihi = __reduce_max_sync(0xffffffffu, hi);
-    }
-    APD_D bool interior(int I, int J) const
-    {
-        return __all_sync(0xffffffffu, lane_tile_interior(lg, rg, I, J));
+        Nlo = __reduce_max_sync(0xffffffffu, nlo);
+        Nhi = __reduce_min_sync(0xffffffffu, nhi);
     }
     APD_D const float4* xaddr(int I) const
     {
         return xbase4 + (ptrdiff_t)(4 * I - rg.rho - 1) * (DPAD / 4) + lane;
     }
-    APD_D void x_preload(int I)
+    APD_D void x_preload(int buf, int I)
     {
         __syncwarp();
-        if (lane < DPAD) xs4[lane] = __ldg(xaddr(I));
-        cur = 0;
+        if (lane < DPAD) xs4[buf * DPAD + lane] = __ldg(xaddr(I));
         __syncwarp();
     }
-    APD_D void x_prefetch(int I)
+    APD_D void x_fetch(int I)
     {
         if (lane < DPAD) xreg = __ldg(xaddr(I));
-        tiles++;
     }
-    APD_D const float* x_tile() const { return reinterpret_cast<const float*>(xs4 + cur * DPAD); }
-    APD_D void x_commit()
+    APD_D void x_commit(int buf)
     {
-        if (lane < DPAD) xs4[(cur ^ 1) * DPAD + lane] = xreg;
-        cur ^= 1;
+        if (lane < DPAD) xs4[buf * DPAD + lane] = xreg;
         __syncwarp();
     }
-    APD_D F2 st_load(int row) const { return st[row * 32]; }
-    APD_D void st_store(int row, F2 v) { st[row * 32] = v; }
-    APD_D void load_y(int J, F2 (&yv)[TILE][DPAD / 2]) const
+    APD_D void note_step(int) const {}
+    APD_D const float* x_tile(int buf) const { return reinterpret_cast<const float*>(xs4 + buf * DPAD); }
+    APD_D void ring_load(int slot, F2 (&v)[TILE]) const
     {
-        const float4* p = ybase4 + (ptrdiff_t)(4 * J - lg.gamma - 1) * (DPAD / 4);
+        const float4 a = ring4[(2 * slot) * 32], b = ring4[(2 * slot + 1) * 32];
+        v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+        v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+    }
+    APD_D void ring_store(int slot, const F2 (&v)[TILE])
+    {
+        ring4[(2 * slot) * 32] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+        ring4[(2 * slot + 1) * 32] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+        tiles++;
+    }
+    APD_D F2 ring_load_last(int slot) const
+    {
+        const float2* p = reinterpret_cast<const float2*>(ring4 + (2 * slot + 1) * 32);
+        return p[1];
+    }
+    APD_D const float4* yaddr(int J) const
+    {
+        return ybase4 + (ptrdiff_t)(4 * J - lg.gamma - 1) * (DPAD / 4);
+    }
+    APD_D void switch_y(int J, F2 (&yv)[TILE][DPAD / 2]) const
+    {
+        if (J < lg.Jt) {
+            const float4* p = yaddr(J);
 #pragma unroll
-        for (int c = 0; c < TILE; c++)
+            for (int c = 0; c < TILE; c++)
 #pragma unroll
-            for (int q = 0; q < DPAD / 4; q++) {
-                float4 v = __ldg(p + c * (DPAD / 4) + q);
-                yv[c][2 * q] = make_float2(v.x, v.y);
-                yv[c][2 * q + 1] = make_float2(v.z, v.w);
-            }
+                for (int q = 0; q < DPAD / 4; q++) {
+                    float4 v = __ldg(p + c * (DPAD / 4) + q);
+                    yv[c][2 * q] = make_float2(v.x, v.y);
+                    yv[c][2 * q + 1] = make_float2(v.z, v.w);
+                }
+        }
+        if (J + 1 < lg.Jt) {  // the next block's frames: pull them towards the SM
+            const char* p = reinterpret_cast<const char*>(yaddr(J + 1));
+#pragma unroll
+            for (int o = 0; o < TILE * DPAD * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + TILE * DPAD * 4 - 4));
+        }
     }
 };
 
@@ -116,10 +142,12 @@ __global__ void __launch_bounds__(32) dtw_units_kernel(const KernelArgs a)
     DevCtx<DPAD> ctx;
     ctx.lane = lane;
     ctx.xs4 = smem4;
-    F2* ring = GSTATE ? a.gstate + (size_t)blockIdx.x * ((size_t)a.St * TILE * 32)
-                      : reinterpret_cast<F2*>(smem4 + 2 * DPAD);
-    ctx.st = ring + lane;
+    float4* ring = GSTATE ? reinterpret_cast<float4*>(a.gstate) + (size_t)blockIdx.x * ((size_t)a.St * 2 * 32)
+                          : smem4 + X_STAGES * DPAD;
+    ctx.ring4 = ring + lane;
     ctx.tiles = 0;
+    for (int k = lane; k < X_STAGES * DPAD; k += 32) smem4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
     const float4* arena4 = reinterpret_cast<const float4*>(a.arena);
 
     for (;;) {
@@ -144,7 +172,13 @@ __global__ void __launch_bounds__(32) dtw_units_kernel(const KernelArgs a)
         } else if (Jt_max > 0) {
             ctx.xbase4 = arena4 + (size_t)a.off[un.a] * (DPAD / 4);
             ctx.ybase4 = arena4 + (size_t)(exists ? a.off[b] : a.off[un.a]) * (DPAD / 4);
-            F2 acc = run_unit<DPAD, STRICT, UNITW>(ctx, ctx.lg, ctx.rg, Jt_max, a.St, a.pen);
+            SqrtFlags fl;
+            flags_reset(fl);
+            F2 acc = run_unit<DPAD, STRICT, UNITW>(ctx, ctx.lg, ctx.rg, Jt_max, a.St, a.pen, fl);
+            if (STRICT && __any_sync(0xffffffffu, ctx.lg.active && flags_bad(fl))) {
+                __syncwarp();
+                acc = run_unit_exact<DPAD, UNITW>(ctx, ctx.lg, ctx.rg, Jt_max, a.St, a.pen);
+            }
             if (ctx.lg.active) {
                 s1 = finish_score(acc.x, n, m);
                 s2 = finish_score(acc.y, n, m);
@@ -183,7 +217,7 @@ APD_DECLARE_DPAD(32)
 
 inline size_t dtw_smem_bytes(int dpad, int St, bool gstate)
 {
-    size_t x = (size_t)2 * 4 * dpad * sizeof(float);
+    size_t x = (size_t)X_STAGES * 4 * dpad * sizeof(float);
     return gstate ? x : x + (size_t)St * TILE * 32 * sizeof(float2);
 }
 

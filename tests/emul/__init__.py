@@ -52,9 +52,9 @@ def align_all(seqs, pct, ins=1.0, dele=1.0, mat=1.0, strict=True, rank=0, world=
         ptrs[k] = s.ctypes.data_as(fp)
     lens = np.array([s.shape[0] for s in seqs], dtype=np.uint32)
     out = np.zeros((n, n), dtype=np.float32)
-    info = np.zeros(12, dtype=np.uint64)
+    info = np.zeros(16, dtype=np.uint64)
     rc = lib().apd_emul_align_all(ptrs, lens.ctypes.data_as(C.POINTER(C.c_uint32)), n, dim, pct, ins,
-                                  dele, mat, 1 if strict else 0, rank, world, out.ctypes.data_as(fp),
+                                  dele, mat, int(strict), rank, world, out.ctypes.data_as(fp),
                                   info.ctypes.data_as(C.POINTER(C.c_uint64)))
     if rc:
         raise RuntimeError("emulator failed: %d" % rc)

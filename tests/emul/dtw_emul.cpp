@@ -26,43 +26,56 @@ struct HostCtx {
     const float* xbase;  // frame 0 of x
     const float* ybase;  // frame 0 of this lane's y
     std::vector<F2> state;
-    const float* cur;
-    const float* nxt;
     uint64_t tiles = 0;
 
-    void row_range(int J, int& Ilo, int& Ihi) const
+    void sweep_info(int J, int& Ilo, int& Ihi, int& Nlo, int& Nhi) const
     {
-        Ilo = 0x3fffffff; Ihi = -1;
+        Ilo = 0x3fffffff; Ihi = -1; Nlo = -0x3fffffff; Nhi = 0x3fffffff;
         for (int l = 0; l < 32; l++) {
-            int lo, hi;
+            int lo, hi, nlo, nhi;
             lane_row_range(lanes[l], rg, J, lo, hi);
+            lane_interior_range(lanes[l], rg, J, nlo, nhi);
             if (lo < Ilo) Ilo = lo;
             if (hi > Ihi) Ihi = hi;
+            if (nlo > Nlo) Nlo = nlo;
+            if (nhi < Nhi) Nhi = nhi;
+        }
+        // cross-check the closed-form interior range against the per-tile predicate
+        for (int I = Ilo; I <= Ihi; I++) {
+            bool all = true;
+            for (int l = 0; l < 32; l++) all = all && lane_tile_interior(lanes[l], rg, I, J);
+            if (all != (I >= Nlo && I <= Nhi)) mismatch = true;
         }
     }
-    bool interior(int I, int J) const
-    {
-        for (int l = 0; l < 32; l++)
-            if (!lane_tile_interior(lanes[l], rg, I, J)) return false;
-        return true;
-    }
     const float* xaddr(int I) const { return xbase + (int64_t)(4 * I - rg.rho - 1) * DPAD; }
-    void x_preload(int I) { cur = xaddr(I); }
-    void x_prefetch(int I) { nxt = xaddr(I); tiles++; }
-    const float* x_tile() const { return cur; }
-    void x_commit() { cur = nxt; }
-    F2 st_load(int row) const { return state[row]; }
-    void st_store(int row, F2 v) { state[row] = v; }
-    void load_y(int J, F2 (&yv)[TILE][DPAD / 2]) const
+    void note_step(int kind) { if (lane == first_lane) steps[kind]++; }
+    void x_preload(int buf, int I) { stage[buf] = xaddr(I); }
+    void x_fetch(int I) { fetched = xaddr(I); }
+    void x_commit(int buf) { stage[buf] = fetched; }
+    // the final pipeline step computes distances of stale rows (discarded): any readable memory will do
+    const float* x_tile(int buf) const { return stage[buf] ? stage[buf] : xaddr(0); }
+    void ring_load(int slot, F2 (&v)[TILE]) const { for (int r = 0; r < TILE; r++) v[r] = state[slot * TILE + r]; }
+    void ring_store(int slot, const F2 (&v)[TILE]) { for (int r = 0; r < TILE; r++) state[slot * TILE + r] = v[r]; tiles++; }
+    F2 ring_load_last(int slot) const { return state[slot * TILE + TILE - 1]; }
+    void switch_y(int J, F2 (&yv)[TILE][DPAD / 2]) const
     {
+        if (J >= lanes[lane].Jt) return;
         const float* p = ybase + (int64_t)(4 * J - lanes[lane].gamma - 1) * DPAD;
         for (int c = 0; c < TILE; c++)
             for (int k = 0; k < DPAD / 2; k++) yv[c][k] = mk2(p[c * DPAD + 2 * k], p[c * DPAD + 2 * k + 1]);
     }
+    const float* stage[3] = {nullptr, nullptr, nullptr};
+    const float* fetched = nullptr;
+    mutable bool mismatch = false;
+    int first_lane = -1;
+    uint64_t* steps = nullptr;
 };
 
+static uint64_t exact_units = 0;
+static uint64_t step_counts[3] = {0, 0, 0};
+
 template <int DPAD>
-int run_all(const Arena& ar, const UnitPlan& plan, float pct, Penalties pen, bool strict,
+int run_all(const Arena& ar, const UnitPlan& plan, float pct, Penalties pen, int strict,
             bool unitw, uint32_t rank, uint32_t world, float* out, uint64_t* tiles_out)
 {
     const uint32_t N = ar.n;
@@ -93,16 +106,28 @@ int run_all(const Arena& ar, const UnitPlan& plan, float pct, Penalties pen, boo
                 } else {
                     HostCtx<DPAD> ctx;
                     ctx.lanes = lanes; ctx.rg = rg; ctx.lane = l;
+                    ctx.steps = step_counts;
+                    for (int q = 0; q < 32 && ctx.first_lane < 0; q++) if (lanes[q].active) ctx.first_lane = q;
                     ctx.xbase = ar.data.data() + (size_t)ar.off[un.a] * DPAD;
                     ctx.ybase = ar.data.data() + (size_t)ar.off[b] * DPAD;
                     F2 poison = mk2(-12345.0f, -54321.0f);  // stale ring entries must never be read
                     ctx.state.assign((size_t)uc.St * TILE, poison);
-                    ctx.cur = ctx.nxt = nullptr;
                     F2 acc;
-                    if (strict && unitw) acc = run_unit<DPAD, true, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen);
-                    else if (strict) acc = run_unit<DPAD, true, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen);
-                    else if (unitw) acc = run_unit<DPAD, false, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen);
-                    else acc = run_unit<DPAD, false, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen);
+                    SqrtFlags fl;
+                    flags_reset(fl);
+                    if (strict && unitw) acc = run_unit<DPAD, true, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
+                    else if (strict) acc = run_unit<DPAD, true, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
+                    else if (unitw) acc = run_unit<DPAD, false, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
+                    else acc = run_unit<DPAD, false, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
+                    // The host sqrt is exact everywhere, so the flags never change a result here;
+                    // strict == 2 forces the cold path so that its schedule is exercised too.
+                    if (strict == 2 || (strict && flags_bad(fl))) {
+                        exact_units++;
+                        ctx.state.assign((size_t)uc.St * TILE, poison);
+                        acc = unitw ? run_unit_exact<DPAD, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen)
+                                    : run_unit_exact<DPAD, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen);
+                    }
+                    if (ctx.mismatch) return -11;  // interior range formula disagrees with the tile predicate
                     s1 = finish_score(acc.x, n, m);
                     s2 = finish_score(acc.y, n, m);
                     if (l == 0 || tiles == 0) tiles += 0;
@@ -123,7 +148,7 @@ int run_all(const Arena& ar, const UnitPlan& plan, float pct, Penalties pen, boo
 extern "C" {
 
 // Emulates apd_align_all (include/apd.h) for shard (rank, world) on the host.
-// info (may be NULL) receives: [0] units, [1] classes, [2] reference cells of the
+// info (may be NULL, 16 entries; [12..14] pipeline steps by mask kind, [15] exact re-runs) receives: [0] units, [1] classes, [2] reference cells of the
 // shard, [3] lane-tiles executed, [4..7] St of up to four classes, [8..11] 1 if gstate.
 int apd_emul_align_all(const float* const* frames, const uint32_t* lens, uint32_t n, uint32_t dim,
                        float pct, float ins, float del, float mat, int strict, uint32_t rank,
@@ -152,11 +177,13 @@ int apd_emul_align_all(const float* const* frames, const uint32_t* lens, uint32_
         default: return -3;
     }
     if (info) {
-        std::memset(info, 0, 12 * sizeof(uint64_t));
+        std::memset(info, 0, 16 * sizeof(uint64_t));
         info[0] = plan.units.size();
         info[1] = plan.classes.size();
         info[2] = reference_cells(ar, plan, rank, world);
         info[3] = tiles;
+        info[12] = step_counts[0]; info[13] = step_counts[1]; info[14] = step_counts[2]; info[15] = exact_units;
+        step_counts[0] = step_counts[1] = step_counts[2] = 0; exact_units = 0;
         for (size_t c = 0; c < plan.classes.size() && c < 4; c++) {
             info[4 + c] = (uint64_t)plan.classes[c].St;
             info[8 + c] = plan.classes[c].gstate ? 1 : 0;

@@ -41,6 +41,16 @@ def test_emulated_schedule_matches_oracle_bitwise(case):
     assert int(info[2]) == ref_cells
 
 
+def test_cold_exact_path_schedule_matches_oracle():
+    """strict=2 forces every unit through run_unit_exact (the generic-sqrt re-run path)."""
+    rng = np.random.default_rng(31)
+    for dim, pct, integer in ((3, 0.2, True), (20, 0.1, False), (8, 1.0, False)):
+        seqs = random_sequences(rng, 37, 1, 45, dim, integer)
+        want = oracle.align_all(seqs, pct, 0.75, 0.5, 1.0, variant="dense")
+        got, _ = emul.align_all(seqs, pct, 0.75, 0.5, 1.0, strict=2)
+        assert np.array_equal(bits(got), bits(want))
+
+
 def test_fast_mode_within_tolerance():
     rng = np.random.default_rng(3)
     seqs = random_sequences(rng, 20, 30, 80, 20, False)
