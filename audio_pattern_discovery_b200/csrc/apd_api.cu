@@ -24,7 +24,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct OccKey { int dpad, strict, unitw, gstate; size_t smem; int occ; };
+struct OccKey { int dpad, strict, unitw, ring; size_t smem; int occ; };
 
 }  // namespace
 
@@ -223,18 +223,18 @@ apd_status ensure_plan(apd_ctx* c, float pct)
     return APD_OK;
 }
 
-apd_status occupancy(apd_ctx* c, const LaunchFns& f, int dpad, bool strict, bool unitw, bool gstate,
+apd_status occupancy(apd_ctx* c, const LaunchFns& f, int dpad, bool strict, bool unitw, int ring,
                      size_t smem, int& occ)
 {
     for (const OccKey& k : c->occ_cache)
-        if (k.dpad == dpad && k.strict == strict && k.unitw == unitw && k.gstate == gstate && k.smem == smem) {
+        if (k.dpad == dpad && k.strict == strict && k.unitw == unitw && k.ring == ring && k.smem == smem) {
             occ = k.occ;
             return APD_OK;
         }
     int o = 0;
-    APD_CUDA(c, f.occ(strict, unitw, gstate, smem, &o));
+    APD_CUDA(c, f.occ(strict, unitw, ring, smem, &o));
     if (o < 1) return fail(c, APD_ERR_INTERNAL, "kernel does not fit on an SM");
-    c->occ_cache.push_back({dpad, strict, unitw, gstate, smem, o});
+    c->occ_cache.push_back({dpad, strict, unitw, ring, smem, o});
     occ = o;
     return APD_OK;
 }
@@ -252,8 +252,14 @@ apd_status run_dtw(apd_ctx* c, const apd_params* p, float* d_packed, cudaStream_
     if (!pick_launcher(c->arena.dpad, f)) return fail(c, APD_ERR_UNSUPPORTED, "unsupported frame width");
     const bool strict = (p->mode == APD_MODE_STRICT);
     const bool unitw = (p->insertion_penalty == 1.0f && p->deletion_penalty == 1.0f && p->match_penalty == 1.0f);
+    // Where the boundary ring lives (dtw_kernels.cuh): tensor memory if it fits 256 columns,
+    // else shared memory, else global scratch.  APD_RING=tmem|smem|global narrows the choice
+    // for experiments and tests (a ring that does not fit the forced home moves down the list).
+    const char* ring_env = getenv("APD_RING");
     const char* force_g = getenv("APD_FORCE_GSTATE");
-    const bool force_gstate = force_g && force_g[0] == '1';
+    int ring_floor = RING_TMEM;  // best allowed: TMEM > SMEM > GLOBAL
+    if (ring_env && !strcmp(ring_env, "smem")) ring_floor = RING_SMEM;
+    if ((ring_env && !strcmp(ring_env, "global")) || (force_g && force_g[0] == '1')) ring_floor = RING_GLOBAL;
 
     APD_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned int), stream));
     APD_CUDA(c, cudaMemsetAsync(c->d_error, 0, sizeof(int), stream));
@@ -267,13 +273,16 @@ apd_status run_dtw(apd_ctx* c, const apd_params* p, float* d_packed, cudaStream_
         k_range(uc.begin, uc.end, c->rank, c->world, k0, k1);
         if (k1 <= k0) continue;
         local_units += k1 - k0;
-        const bool gstate = uc.gstate || force_gstate;
-        const size_t smem = dtw_smem_bytes((int)c->arena.dpad, uc.St, gstate);
+        int ring = RING_GLOBAL;
+        if (ring_floor == RING_TMEM && uc.St <= TMEM_RING_TILES) ring = RING_TMEM;
+        else if (ring_floor != RING_GLOBAL && !uc.gstate) ring = RING_SMEM;
+        const size_t smem = dtw_smem_bytes((int)c->arena.dpad, uc.St, ring);
         if (smem > c->smem_optin) return fail(c, APD_ERR_INTERNAL, "ring does not fit in shared memory");
         int occ = 0;
-        apd_status s = occupancy(c, f, (int)c->arena.dpad, strict, unitw, gstate, smem, occ);
+        apd_status s = occupancy(c, f, (int)c->arena.dpad, strict, unitw, ring, smem, occ);
         if (s != APD_OK) return s;
-        uint64_t grid64 = std::min<uint64_t>(k1 - k0, (uint64_t)c->sm_count * occ);
+        const uint64_t warps_per_cta = (uint64_t)dtw_cta_warps(ring);
+        uint64_t grid64 = std::min<uint64_t>((k1 - k0 + warps_per_cta - 1) / warps_per_cta, (uint64_t)c->sm_count * occ);
         int grid = (int)grid64;
         KernelArgs a{};
         a.arena = c->d_arena; a.off = c->d_off; a.len = c->d_len; a.units = c->d_units;
@@ -286,13 +295,17 @@ apd_status run_dtw(apd_ctx* c, const apd_params* p, float* d_packed, cudaStream_
         a.out = reinterpret_cast<float2*>(d_packed);
         a.error_flag = c->d_error;
         a.tiles_done = c->d_tiles;
-        if (gstate) {
+        if (ring == RING_GLOBAL) {
             size_t need = (size_t)grid * uc.St * TILE * 32;
             s = ensure_device(c, c->d_gstate, c->gstate_cap, need);
             if (s != APD_OK) return s;
             a.gstate = c->d_gstate;
         }
-        APD_CUDA(c, f.launch(a, strict, unitw, gstate, grid, smem, stream));
+        if (getenv("APD_DEBUG"))
+            fprintf(stderr, "[apd] class %zu: ring=%s St=%d units=%llu grid=%d x %d warps occ=%d smem=%zu\n", ci,
+                    ring == RING_TMEM ? "tmem" : (ring == RING_SMEM ? "smem" : "global"), uc.St,
+                    (unsigned long long)(k1 - k0), grid, (int)warps_per_cta, occ, smem);
+        APD_CUDA(c, f.launch(a, strict, unitw, ring, grid, smem, stream));
         launches++;
     }
     APD_CUDA(c, cudaEventRecord(c->ev_k1, stream));

@@ -13,9 +13,16 @@
 //   ring : St tiles x 2 halves x 32 lanes x float4 -- boundary column of the previous
 //          column block ((D1, D2) of 2 rows per float4), lane-contiguous so LDS.128 /
 //          STS.128 are conflict-free.
-// GSTATE kernels keep the ring in a per-CTA slice of a global scratch buffer
-// instead (same layout, coalesced 256-byte rows, L2 resident) for bands too wide
-// for shared memory.
+// Where the ring lives is a kernel variant (RING_*):
+//   RING_TMEM    in Blackwell tensor memory: each lane owns one TMEM lane of its warp's
+//                32-lane quadrant, a ring tile is 8 consecutive 32-bit columns moved with
+//                tcgen05.st / tcgen05.ld (.32x32b.x8).  TMEM is otherwise idle here (no
+//                MMA), it costs no shared memory and no L2 traffic, and leaves occupancy to
+//                the register file: CTAs of 4 warps, 256 columns each, 2 CTAs per SM.
+//   RING_SMEM    in shared memory (layout above), single-warp CTAs; bands too tall for
+//                256 TMEM columns.
+//   RING_GLOBAL  in a per-warp slice of a global scratch buffer (same layout, coalesced
+//                512-byte rows, L2 resident); bands too tall for shared memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -47,8 +54,10 @@ struct KernelArgs {
 #if defined(__CUDACC__)
 
 enum { X_STAGES = 3 };  // x row-tile stage buffers per warp
+enum { RING_SMEM = 0, RING_GLOBAL = 1, RING_TMEM = 2 };
+enum { TMEM_WARPS = 4, TMEM_COLS = 256, TMEM_RING_TILES = TMEM_COLS / 8 };
 
-template <int DPAD>
+template <int DPAD, int RING>
 struct DevCtx {
     LaneGeom lg;
     RowGeom rg;
@@ -57,6 +66,8 @@ struct DevCtx {
     const float4* ybase4;  // frame 0 of this lane's y
     float4* xs4;           // X_STAGES x DPAD float4
     float4* ring4;         // this lane's ring column: tile s, half h at ring4[(2 * s + h) * 32]
+    int St;                // ring size in tiles
+    uint32_t taddr;        // RING_TMEM: (first lane of the warp's quadrant << 16) | first column
     float4 xreg;
     unsigned int tiles;
 
@@ -93,18 +104,68 @@ struct DevCtx {
     APD_D const float* x_tile(int buf) const { return reinterpret_cast<const float*>(xs4 + buf * DPAD); }
     APD_D void ring_load(int slot, F2 (&v)[TILE]) const
     {
-        const float4 a = ring4[(2 * slot) * 32], b = ring4[(2 * slot + 1) * 32];
-        v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
-        v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+        if (RING == RING_TMEM) {
+            // Outputs go straight into v's registers: nothing may read them before ring_wait().
+            asm volatile(
+                "tcgen05.wait::st.sync.aligned;\n"
+                "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x),
+                  "=f"(v[3].y)
+                : "r"(taddr + 8u * (uint32_t)slot));
+        } else {
+            const float4 a = ring4[(2 * slot) * 32], b = ring4[(2 * slot + 1) * 32];
+            v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
+            v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+            if (RING == RING_GLOBAL) {
+                // Rings this tall (unbanded long pairs: up to 1 MB per warp) stream from L2 / HBM;
+                // they are walked sequentially, so pull the tile 4 steps ahead into L1 now.
+                int sp = slot + 4;
+                if (sp >= St) sp -= St;
+                if (sp < St) {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ring4 + (2 * sp) * 32));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ring4 + (2 * sp + 1) * 32));
+                }
+            }
+        }
     }
+    // The tile requested by ring_load() may not be read before this (a no-op for the
+    // scoreboarded shared / global loads; the registers are tied to the wait for TMEM).
+    APD_D void ring_wait(F2 (&v)[TILE]) const
+    {
+        if (RING == RING_TMEM) {
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                         : "+f"(v[0].x), "+f"(v[0].y), "+f"(v[1].x), "+f"(v[1].y), "+f"(v[2].x), "+f"(v[2].y),
+                           "+f"(v[3].x), "+f"(v[3].y));
+        }
+    }
+    // Completion of the store is awaited by the next ring_load (tcgen05.wait::st there).
     APD_D void ring_store(int slot, const F2 (&v)[TILE])
     {
-        ring4[(2 * slot) * 32] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
-        ring4[(2 * slot + 1) * 32] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+        if (RING == RING_TMEM) {
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+                :
+                : "r"(taddr + 8u * (uint32_t)slot), "r"(__float_as_uint(v[0].x)), "r"(__float_as_uint(v[0].y)),
+                  "r"(__float_as_uint(v[1].x)), "r"(__float_as_uint(v[1].y)), "r"(__float_as_uint(v[2].x)),
+                  "r"(__float_as_uint(v[2].y)), "r"(__float_as_uint(v[3].x)), "r"(__float_as_uint(v[3].y)));
+        } else {
+            ring4[(2 * slot) * 32] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+            ring4[(2 * slot + 1) * 32] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+        }
         tiles++;
     }
     APD_D F2 ring_load_last(int slot) const
     {
+        if (RING == RING_TMEM) {
+            uint32_t r0, r1;
+            asm volatile(
+                "tcgen05.wait::st.sync.aligned;\n"
+                "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n"
+                "tcgen05.wait::ld.sync.aligned;\n"
+                : "=r"(r0), "=r"(r1)
+                : "r"(taddr + 8u * (uint32_t)slot + 6u));
+            return make_float2(__uint_as_float(r0), __uint_as_float(r1));
+        }
         const float2* p = reinterpret_cast<const float2*>(ring4 + (2 * slot + 1) * 32);
         return p[1];
     }
@@ -134,22 +195,12 @@ struct DevCtx {
     }
 };
 
-template <int DPAD, bool STRICT, bool UNITW, bool GSTATE>
-__global__ void __launch_bounds__(32) dtw_units_kernel(const KernelArgs a)
+// The persistent work loop of one warp: pulls 32-pair units from the class counter.
+template <int DPAD, bool STRICT, bool UNITW, int RING>
+APD_D void warp_unit_loop(const KernelArgs& a, DevCtx<DPAD, RING>& ctx)
 {
-    extern __shared__ float4 smem4[];
-    const int lane = threadIdx.x;
-    DevCtx<DPAD> ctx;
-    ctx.lane = lane;
-    ctx.xs4 = smem4;
-    float4* ring = GSTATE ? reinterpret_cast<float4*>(a.gstate) + (size_t)blockIdx.x * ((size_t)a.St * 2 * 32)
-                          : smem4 + X_STAGES * DPAD;
-    ctx.ring4 = ring + lane;
-    ctx.tiles = 0;
-    for (int k = lane; k < X_STAGES * DPAD; k += 32) smem4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
+    const int lane = ctx.lane;
     const float4* arena4 = reinterpret_cast<const float4*>(a.arena);
-
     for (;;) {
         unsigned int k = 0;
         if (lane == 0) k = atomicAdd(a.counter, 1u);
@@ -193,18 +244,75 @@ __global__ void __launch_bounds__(32) dtw_units_kernel(const KernelArgs a)
     }
 }
 
+// RING_SMEM / RING_GLOBAL: single-warp CTAs.
+template <int DPAD, bool STRICT, bool UNITW, int RING>
+__global__ void __launch_bounds__(32) dtw_units_kernel(const KernelArgs a)
+{
+    extern __shared__ float4 smem4[];
+    const int lane = threadIdx.x;
+    DevCtx<DPAD, RING> ctx;
+    ctx.lane = lane;
+    ctx.xs4 = smem4;
+    float4* ring = (RING == RING_GLOBAL) ? reinterpret_cast<float4*>(a.gstate) + (size_t)blockIdx.x * ((size_t)a.St * 2 * 32)
+                                         : smem4 + X_STAGES * DPAD;
+    ctx.ring4 = ring + lane;
+    ctx.taddr = 0;
+    ctx.St = a.St;
+    ctx.tiles = 0;
+    for (int k = lane; k < X_STAGES * DPAD; k += 32) smem4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    warp_unit_loop<DPAD, STRICT, UNITW, RING>(a, ctx);
+}
+
+// RING_TMEM: CTAs of TMEM_WARPS independent warps sharing one tensor-memory allocation of
+// TMEM_COLS columns; warp w owns the TMEM lanes 32w .. 32w+31 (the only ones tcgen05.ld/st
+// issued by that warp can reach), lane l of the warp owns TMEM lane 32w + l.
+template <int DPAD, bool STRICT, bool UNITW>
+__global__ void __launch_bounds__(32 * TMEM_WARPS, 2) dtw_units_tmem_kernel(const KernelArgs a)
+{
+    extern __shared__ float4 smem4[];
+    __shared__ uint32_t tmem_base_smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_smem);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst), "r"((uint32_t)TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    DevCtx<DPAD, RING_TMEM> ctx;
+    ctx.lane = lane;
+    ctx.xs4 = smem4 + warp * (X_STAGES * DPAD);
+    ctx.ring4 = nullptr;
+    ctx.taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+    ctx.St = a.St;
+    ctx.tiles = 0;
+    for (int k = lane; k < X_STAGES * DPAD; k += 32) ctx.xs4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+    warp_unit_loop<DPAD, STRICT, UNITW, RING_TMEM>(a, ctx);
+
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+    }
+}
+
 #endif  // __CUDACC__
 
 // Per-DPAD launchers (dtw_inst.cu, one object per padded frame width).
-typedef cudaError_t (*dtw_launch_fn)(const KernelArgs& a, bool strict, bool unitw, bool gstate,
+typedef cudaError_t (*dtw_launch_fn)(const KernelArgs& a, bool strict, bool unitw, int ring,
                                      int grid, size_t smem, cudaStream_t stream);
-typedef cudaError_t (*dtw_occupancy_fn)(bool strict, bool unitw, bool gstate, size_t smem,
+typedef cudaError_t (*dtw_occupancy_fn)(bool strict, bool unitw, int ring, size_t smem,
                                         int* blocks_per_sm);
 
 #define APD_DECLARE_DPAD(D)                                                                    \
-    cudaError_t dtw_launch_##D(const KernelArgs& a, bool strict, bool unitw, bool gstate,      \
+    cudaError_t dtw_launch_##D(const KernelArgs& a, bool strict, bool unitw, int ring,         \
                                int grid, size_t smem, cudaStream_t stream);                    \
-    cudaError_t dtw_occupancy_##D(bool strict, bool unitw, bool gstate, size_t smem,           \
+    cudaError_t dtw_occupancy_##D(bool strict, bool unitw, int ring, size_t smem,              \
                                   int* blocks_per_sm);
 APD_DECLARE_DPAD(4)
 APD_DECLARE_DPAD(8)
@@ -215,10 +323,13 @@ APD_DECLARE_DPAD(24)
 APD_DECLARE_DPAD(28)
 APD_DECLARE_DPAD(32)
 
-inline size_t dtw_smem_bytes(int dpad, int St, bool gstate)
+// Dynamic shared memory per CTA (one warp, or TMEM_WARPS warps for RING_TMEM).
+inline size_t dtw_smem_bytes(int dpad, int St, int ring)
 {
     size_t x = (size_t)X_STAGES * 4 * dpad * sizeof(float);
-    return gstate ? x : x + (size_t)St * TILE * 32 * sizeof(float2);
+    if (ring == RING_TMEM) return x * TMEM_WARPS;
+    return ring == RING_GLOBAL ? x : x + (size_t)St * TILE * 32 * sizeof(float2);
 }
+inline int dtw_cta_warps(int ring) { return ring == RING_TMEM ? TMEM_WARPS : 1; }
 
 }  // namespace apd

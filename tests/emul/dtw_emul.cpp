@@ -55,6 +55,7 @@ struct HostCtx {
     // the final pipeline step computes distances of stale rows (discarded): any readable memory will do
     const float* x_tile(int buf) const { return stage[buf] ? stage[buf] : xaddr(0); }
     void ring_load(int slot, F2 (&v)[TILE]) const { for (int r = 0; r < TILE; r++) v[r] = state[slot * TILE + r]; }
+    void ring_wait(F2 (&)[TILE]) const {}
     void ring_store(int slot, const F2 (&v)[TILE]) { for (int r = 0; r < TILE; r++) state[slot * TILE + r] = v[r]; tiles++; }
     F2 ring_load_last(int slot) const { return state[slot * TILE + TILE - 1]; }
     void switch_y(int J, F2 (&yv)[TILE][DPAD / 2]) const
