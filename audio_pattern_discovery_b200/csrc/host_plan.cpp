@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "dtw_core.h"
 
@@ -42,20 +43,47 @@ std::string build_arena_layout(const uint32_t* lens, uint32_t n, uint32_t dim, A
     return "";
 }
 
-void fill_arena(const Arena& ar, const float* const* frames, float* dst)
+static void fill_arena_range(const Arena& ar, const float* const* frames, float* dst, uint32_t s0, uint32_t s1)
 {
-    std::memset(dst, 0, (size_t)ar.total_frames * ar.dpad * sizeof(float));
-    for (uint32_t s = 0; s < ar.n; s++) {
+    for (uint32_t s = s0; s < s1; s++) {
+        // zero the pre-pad in front of the sequence (and the slack behind the last one)
+        float* pad = dst + (size_t)(ar.off[s] - PRE_PAD_FRAMES) * ar.dpad;
+        std::memset(pad, 0, (size_t)PRE_PAD_FRAMES * ar.dpad * sizeof(float));
+        if (s + 1 == ar.n)
+            std::memset(dst + (size_t)(ar.off[s] + ar.len[s]) * ar.dpad, 0, (size_t)PRE_PAD_FRAMES * ar.dpad * sizeof(float));
         const float* src = frames[ar.perm[s]];
         float* d = dst + (size_t)ar.off[s] * ar.dpad;
         if (!ar.len[s]) continue;
         if (ar.dpad == ar.dim) {
             std::memcpy(d, src, (size_t)ar.len[s] * ar.dim * sizeof(float));
         } else {
-            for (uint32_t t = 0; t < ar.len[s]; t++)
-                std::memcpy(d + (size_t)t * ar.dpad, src + (size_t)t * ar.dim, ar.dim * sizeof(float));
+            for (uint32_t t = 0; t < ar.len[s]; t++) {
+                float* row = d + (size_t)t * ar.dpad;
+                std::memcpy(row, src + (size_t)t * ar.dim, ar.dim * sizeof(float));
+                for (uint32_t k = ar.dim; k < ar.dpad; k++) row[k] = 0.0f;
+            }
         }
     }
+}
+
+void fill_arena(const Arena& ar, const float* const* frames, float* dst)
+{
+    if (ar.n == 0) {
+        std::memset(dst, 0, (size_t)ar.total_frames * ar.dpad * sizeof(float));
+        return;
+    }
+    // The copy is memory bound; a few host threads get it close to the DRAM rate.
+    const uint64_t bytes = (uint64_t)ar.total_frames * ar.dpad * sizeof(float);
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = std::max(1u, std::min(nt, 8u));
+    if (bytes < (8u << 20) || ar.n < 2 * nt) nt = 1;
+    if (nt == 1) { fill_arena_range(ar, frames, dst, 0, ar.n); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) {
+        const uint32_t s0 = (uint32_t)((uint64_t)ar.n * t / nt), s1 = (uint32_t)((uint64_t)ar.n * (t + 1) / nt);
+        th.emplace_back([&ar, frames, dst, s0, s1] { fill_arena_range(ar, frames, dst, s0, s1); });
+    }
+    for (auto& x : th) x.join();
 }
 
 std::string build_arena(const float* const* frames, const uint32_t* lens, uint32_t n,

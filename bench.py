@@ -2,7 +2,7 @@
 """bench.py -- BASELINE.json's metric: DTW GCUPS (1e9 reference cell updates / s) and
 all-pairs matrix wall time for the banded weighted DTW distance matrix.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C2|C4|C5] [--n SEQS]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3|C2|C4|C5] [--seqs SEQS]
                     [--mode strict|fast] [--impl b200|reference]
 
 One "step" = one full all-pairs matrix (every ordered pair, both orientations) of the
@@ -181,7 +181,7 @@ def run_reference(args):
                                         "(static row blocks, one thread per core), gcc -O2",
                              "literal_hashmap_gcups": lit["gcups"], "literal_sample_sequences": lit["S"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -295,6 +295,13 @@ def run_b200(args):
     e2e_gcups = cells_total / (e2e_ms_step / 1e3) / 1e9
     h2d = al.stats()["h2d_bytes"]
 
+    other = None
+    if args.other_mode_steps > 0:
+        omode = APD_MODE_FAST if strict else APD_MODE_STRICT
+        other = measure_other_mode(seqs, c, local, omode, args.other_mode_steps, cells_total, world, maxrank, barrier,
+                                   need_flush, flush)
+        other["mode"] = "fast" if strict else "strict"
+
     line = None
     if rank == 0:
         sm_count = st["sm_count"]
@@ -314,6 +321,7 @@ def run_b200(args):
             "e2e": {"value": e2e_gcups, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(n * n * 4), "steps": e2e_steps, "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches),
+            "other_mode": other,
             "clocks": clocks,
             "roofline": {
                 "bound": "fp32-issue", "kernel": "dtw_units_kernel (%s)" % args.mode,
@@ -321,7 +329,14 @@ def run_b200(args):
                 "frac_at_observed_clock": achieved / peak_obs, "observed_sm_mhz": clk_mhz,
                 "peak_source": "%d SMs x 128 FP32 lanes x %s sm_max_mhz (%s MEASURED_PEAKS.json)" % (
                     sm_count, peaks.get("sm_max_mhz"), peaks_src),
-                "instr_per_cell": icell, "kernel_ms_per_step": kernel_ms_avg, "dtw_launches_per_step": dtw_launches,
+                "instr_per_cell": icell,
+                "fma_pipe_model": {"cycles_per_ordered_cell": (1.625 * c["dim"] if strict else c["dim"]) + 1.5,
+                                   "frac_of_fma_pipe_at_max_clock":
+                                       cells_local * ((1.625 * c["dim"] if strict else c["dim"]) + 1.5)
+                                       / (kernel_ms_avg / 1e3) / (sm_count * 4 * 32 * peaks.get("sm_max_mhz", 1965.0) * 1e6),
+                                   "note": "f32x2 ops occupy the 32-lane FMA pipe for 2 cycles (measured: "
+                                           "profiles/r1_microbench*.txt); DESIGN.md section 4"},
+                "kernel_ms_per_step": kernel_ms_avg, "dtw_launches_per_step": dtw_launches,
                 "cells_per_step_this_gpu": int(cells_local), "scatter_ms_per_step": float(np.mean(scat_ms)),
                 "traffic": None,
                 "hbm": {"algorithmic_bytes": int(arena_bytes + 2 * n * n * 4),
@@ -338,23 +353,67 @@ def run_b200(args):
                 "variant": "oracle dense rolling-band restatement, reference threading scheme, gcc -O2",
                 "literal_hashmap_gcups": lit["gcups"], "literal_sample_sequences": lit["S"],
                 "full_matrix_extrapolated_s": cells_total / (info["gcups"] * 1e9)}
-        print(json.dumps(line), flush=True)
+        emit(line)
     al.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+def measure_other_mode(seqs, c, local, mode, steps, cells_total, world, maxrank, barrier, need_flush, flush):
+    """Device-resident GCUPS of the other arithmetic variant (reported beside the headline)."""
+    import torch
+    from audio_pattern_discovery_b200.distributed import ShardedAligner
+    ins, dele, mat = c["weights"]
+    al = ShardedAligner(seqs, device=local, mode=mode)
+    al.align_all_device(c["pct"], ins, dele, mat)
+    al.synchronize()
+    barrier()
+    ms = []
+    for _ in range(steps):
+        if need_flush:
+            flush.fill_(1.0)
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(al.stream)
+        al.align_all_device(c["pct"], ins, dele, mat)
+        e1.record(al.stream)
+        al.synchronize()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    barrier()
+    kernel_ms = al.stats()["kernel_ms"]
+    al.close()
+    t = maxrank(float(sum(ms))) / steps
+    return {"gcups": cells_total / (t / 1e3) / 1e9, "ms_per_step": t, "steps": steps, "kernel_ms": kernel_ms}
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints to
+    fd 1 (e.g. NCCL's version banner) was redirected to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3", choices=["C2", "C3", "C4", "C5"])
-    ap.add_argument("--n", type=int, default=None, help="override the number of sequences")
+    ap.add_argument("--seqs", dest="n", type=int, default=None, help="override the number of sequences")
     ap.add_argument("--mode", default="strict", choices=["strict", "fast"])
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--other-mode-steps", type=int, default=2,
+                    help="timed steps of the other arithmetic variant, reported beside the headline (0 = skip)")
     ap.add_argument("--ref-seconds", type=float, default=15.0)
     ap.add_argument("--ref-max-seqs", type=int, default=384)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

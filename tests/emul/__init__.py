@@ -18,7 +18,7 @@ def build():
     if os.path.exists(_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(_OUT) for d in deps):
         return _OUT
     os.makedirs(os.path.dirname(_OUT), exist_ok=True)
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-pthread",
            "-o", _OUT] + srcs
     subprocess.run(cmd, check=True, capture_output=True)
     return _OUT
