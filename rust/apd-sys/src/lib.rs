@@ -1,0 +1,70 @@
+//! Raw bindings of include/apd.h (ABI version 1).  One declaration per exported symbol;
+//! the reference interface each one replaces is cited in the header.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+pub const APD_OK: c_int = 0;
+pub const APD_ERR_NO_DEVICE: c_int = 2;
+pub const APD_MODE_STRICT: u32 = 0;
+pub const APD_MODE_FAST: u32 = 1;
+pub const APD_MAX_DIM: u32 = 32;
+
+#[repr(C)]
+pub struct apd_ctx {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct apd_params {
+    pub warping_band_percentage: f32,
+    pub insertion_penalty: f32,
+    pub deletion_penalty: f32,
+    pub match_penalty: f32,
+    pub mode: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct apd_stats {
+    pub n_sequences: u64,
+    pub ordered_pairs: u64,
+    pub units_total: u64,
+    pub units_local: u64,
+    pub cells_reference: u64,
+    pub cells_computed: u64,
+    pub kernel_launches: u32,
+    pub kernel_ms: f32,
+    pub scatter_ms: f32,
+    pub h2d_ms: f32,
+    pub d2h_ms: f32,
+    pub h2d_bytes: u64,
+    pub d2h_bytes: u64,
+    pub sm_clock_mhz: f32,
+    pub sm_count: u32,
+}
+
+extern "C" {
+    pub fn apd_abi_version() -> u32;
+    pub fn apd_create(device_id: c_int, out: *mut *mut apd_ctx) -> c_int;
+    pub fn apd_destroy(ctx: *mut apd_ctx);
+    pub fn apd_last_error(ctx: *const apd_ctx) -> *const c_char;
+    pub fn apd_set_sequences(ctx: *mut apd_ctx, frames: *const *const f32, lens: *const u32, n: u32, dim: u32) -> c_int;
+    pub fn apd_set_sequences_flat(ctx: *mut apd_ctx, flat: *const f32, offsets: *const u64, lens: *const u32, n: u32,
+                                  dim: u32) -> c_int;
+    pub fn apd_set_shard(ctx: *mut apd_ctx, rank: u32, world: u32) -> c_int;
+    pub fn apd_align_all(ctx: *mut apd_ctx, p: *const apd_params, out_nxn: *mut f32) -> c_int;
+    pub fn apd_packed_len(ctx: *mut apd_ctx, p: *const apd_params, n_floats: *mut u64) -> c_int;
+    pub fn apd_align_packed(ctx: *mut apd_ctx, p: *const apd_params, d_packed: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn apd_scatter_packed(ctx: *mut apd_ctx, d_gathered: *const f32, world: u32, d_out_nxn: *mut f32,
+                              stream: *mut c_void) -> c_int;
+    pub fn apd_synchronize(ctx: *mut apd_ctx, stream: *mut c_void) -> c_int;
+    pub fn apd_align_pair(ctx: *mut apd_ctx, p: *const apd_params, i: u32, j: u32, score: *mut f32, path_ij: *mut u32,
+                          path_cap: u64, path_len: *mut u64) -> c_int;
+    pub fn apd_align_pairs(ctx: *mut apd_ctx, p: *const apd_params, pairs_ij: *const u32, n_pairs: u64,
+                           scores: *mut f32, paths_ij: *mut u32, path_cap: u64, path_lens: *mut u64) -> c_int;
+    pub fn apd_align_pairs_band(ctx: *mut apd_ctx, p: *const apd_params, warping_band: u64, pairs_ij: *const u32,
+                                n_pairs: u64, scores: *mut f32, paths_ij: *mut u32, path_cap: u64,
+                                path_lens: *mut u64) -> c_int;
+    pub fn apd_get_stats(ctx: *mut apd_ctx, out: *mut apd_stats) -> c_int;
+}
