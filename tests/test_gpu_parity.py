@@ -251,3 +251,107 @@ def test_upgma_handoff_identical_merges():
     if not any(t for *_, t in m_want):
         assert [frozenset((a, b)) for a, b, *_ in m_fast] == [frozenset((a, b)) for a, b, *_ in m_want]
         assert np.array_equal(a_fast, a_want)
+
+
+@pytest.mark.parametrize("ring", ["tmem", "smem", "global"])
+def test_ring_homes_agree_bitwise(ring, monkeypatch):
+    """The boundary ring in tensor memory, shared memory and global scratch: same bits."""
+    from audio_pattern_discovery_b200 import synth
+    seqs, _ = synth.make_sequences(130, 300, 20, 5, 91)
+    want = oracle.align_all(seqs, 0.1, workers=8, variant="dense")
+    monkeypatch.setenv("APD_RING", ring)
+    got, _ = gpu_matrix(seqs, 0.1)
+    assert np.array_equal(bits(got), bits(want))
+    fast, _ = gpu_matrix(seqs, 0.1, fast=True)
+    assert_close(fast, want)
+
+
+def test_tiny_magnitudes_take_the_exact_sqrt_path():
+    """Squared distances below 2^-101 (and subnormal ones) are outside the hot path's square
+    root: the unit re-runs with the generic IEEE sqrt and stays bit-exact."""
+    rng = np.random.default_rng(17)
+    seqs = [(rng.normal(size=(int(t), 4)) * 1e-19).astype(np.float32) for t in rng.integers(5, 40, size=20)]
+    seqs += [(rng.normal(size=(int(t), 4)) * 1e-16).astype(np.float32) for t in rng.integers(5, 40, size=20)]
+    want = oracle.align_all(seqs, 0.3, workers=8, variant="dense")
+    got, _ = gpu_matrix(seqs, 0.3)
+    assert np.array_equal(bits(got), bits(want))
+    big = [(s * np.float32(1e36)).astype(np.float32) for s in seqs[20:]]  # 1e20 magnitudes: squares overflow to INF
+    want = oracle.align_all(big, 0.3, workers=8, variant="dense")
+    got, _ = gpu_matrix(big, 0.3)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    f = ~np.isnan(want)
+    assert np.array_equal(bits(got[f]), bits(want[f]))
+
+
+def test_c1_shaped_reference_defaults_and_upgma():
+    """BASELINE.json config 1 at the DTW boundary: ~auto-encoder embeddings (dim 10, per-frame
+    z-scored), slices of >= 150 frames, the reference's default Discovery.toml (band 100 %,
+    unit penalties, clustering_percentile 0.05): matrix bits and UPGMA merges."""
+    from audio_pattern_discovery_b200 import AlignmentWorkers, Discovery, NDSequence, synth
+    rng = np.random.default_rng(18)
+    seqs, _ = synth.make_sequences(80, rng.integers(150, 260, size=80), 10, 7, 1001, zscore=True)
+    nd = [NDSequence.from_array(s) for s in seqs]
+    d = Discovery()  # project/config/Discovery.toml defaults
+    w = AlignmentWorkers.new(nd)
+    w.align_all(d)
+    got = w.result.lock().unwrap().reshape(80, 80)
+    want = oracle.align_all(seqs, d.warping_band_percentage, workers=8, variant="dense")
+    assert np.array_equal(bits(got), bits(want))
+    mg, tg, ag = oracle.upgma(got, d.clustering_percentile)
+    mw, tw, aw = oracle.upgma(want, d.clustering_percentile)
+    assert tg == tw and [(a, b, k) for a, b, k, _, _ in mg] == [(a, b, k) for a, b, k, _, _ in mw]
+    assert np.array_equal(ag, aw)
+
+
+def test_c5_shaped_long_unbanded_pairs_and_paths():
+    """BASELINE.json config 5 shape: len 4096, dim 20, unbanded; a few sequences, spot-checked
+    pairs, and device-traced warping paths on shorter unbanded pairs."""
+    from audio_pattern_discovery_b200 import Context, synth
+    seqs, _ = synth.make_sequences(10, 4096, 20, 3, 1005)
+    got, _ = gpu_matrix(seqs, 1.0)
+    pairs = np.array([(0, 1), (1, 0), (3, 7), (9, 2), (4, 5), (8, 6)], dtype=np.uint32)
+    want = oracle.align_pairs(seqs, pairs, 1.0, workers=6)
+    assert np.array_equal(bits(got[pairs[:, 0], pairs[:, 1]]), bits(want))
+    short, _ = synth.make_sequences(6, np.array([700, 650, 700, 512, 900, 700]), 20, 2, 1006)
+    with Context(0) as c:
+        c.set_sequences(short)
+        prs = [(0, 1), (2, 5), (4, 3)]
+        scores, paths, lens = c.align_pairs(prs, 1.0, want_paths=True, path_cap=2000)
+    for (i, j), s, p, ln in zip(prs, scores, paths, lens):
+        ws, wp = oracle.dtw(short[i], short[j], 1.0, want_path=True)
+        assert bits(s)[0] == bits(ws)[0]
+        assert ln == len(wp) and np.array_equal(p, wp)
+
+
+def test_full_c3_matrix_spot_check_and_properties():
+    """BASELINE.json config 3 at full size (10 000 x len 512 x dim 20, band 10 %): 1e8 ordered
+    pairs on the GPU; random pairs against the oracle (bit-exact), FAST within 1e-5 of STRICT
+    on every entry, and size-independent properties."""
+    from audio_pattern_discovery_b200 import APD_MODE_FAST, Context, synth
+    c, seqs, _ = synth.make_config("C3")
+    seqs[4321] = seqs[77].copy()
+    n = len(seqs)
+    with Context(0) as ctx:
+        ctx.set_sequences(seqs)
+        strict = ctx.align_all(c["pct"], *c["weights"])
+        st = ctx.stats()
+        fast = ctx.align_all(c["pct"], *c["weights"], mode=APD_MODE_FAST)
+    assert st["ordered_pairs"] == n * (n - 1)
+    assert st["cells_reference"] == n * (n - 1) * 51463          # SURVEY.md Appendix C
+    assert np.all(np.diag(strict) == 0.0)
+    assert strict[77, 4321] == 0.0 and strict[4321, 77] == 0.0
+    assert np.all(np.isfinite(strict)) and strict.min() >= 0.0
+    off = ~np.eye(n, dtype=bool)
+    nz = off & (strict > 0)
+    rel = np.abs(fast[nz] - strict[nz]) / strict[nz]
+    assert rel.max() <= REL_TOL, rel.max()
+    # rows of the duplicate pair agree entry by entry (same sequence, same partners)
+    m = np.ones(n, dtype=bool)
+    m[[77, 4321]] = False
+    assert np.array_equal(bits(strict[77, m]), bits(strict[4321, m]))
+    assert np.array_equal(bits(strict[m, 77]), bits(strict[m, 4321]))
+    rng = np.random.default_rng(19)
+    pairs = rng.integers(0, n, size=(1500, 2))
+    pairs = pairs[pairs[:, 0] != pairs[:, 1]]
+    want = oracle.align_pairs(seqs, pairs, c["pct"], *c["weights"], workers=8)
+    assert np.array_equal(bits(strict[pairs[:, 0], pairs[:, 1]]), bits(want))
