@@ -102,11 +102,14 @@ class Context:
         for a in arrs:
             if a.shape[0] and a.shape[1] != dim:
                 raise ValueError("all sequences must share the frame width")
-        ptrs = (_fp * max(n, 1))()
-        for k, a in enumerate(arrs):
-            ptrs[k] = a.ctypes.data_as(_fp)
-        lens = np.array([a.shape[0] for a in arrs], dtype=np.uint32)
+        # one pointer per sequence, built without a ctypes object per element
+        addr = np.fromiter((a.__array_interface__["data"][0] for a in arrs), dtype=np.uintp, count=n)
+        if n == 0:
+            addr = np.zeros(1, dtype=np.uintp)
+        ptrs = addr.ctypes.data_as(C.POINTER(_fp))
+        lens = np.fromiter((a.shape[0] for a in arrs), dtype=np.uint32, count=n)
         self._check(self._lib.apd_set_sequences(self._h, ptrs, lens.ctypes.data_as(_u32p), n, dim))
+        self._keepalive = arrs  # the library copies before returning; kept only until the next call
         self.n, self.dim = n, dim
 
     def set_sequences_flat(self, flat, offsets, lens, dim):

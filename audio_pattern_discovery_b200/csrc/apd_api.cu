@@ -184,11 +184,21 @@ apd_status begin_sequences(apd_ctx* c, const uint32_t* lens, uint32_t n, uint32_
     if (dim > APD_MAX_DIM) return fail(c, APD_ERR_UNSUPPORTED, "dim > APD_MAX_DIM (32) is not supported");
     if (n > 0 && !lens) return fail(c, APD_ERR_INVALID, "lens is NULL");
     APD_CUDA(c, cudaSetDevice(c->device));
+    const bool had = c->have_sequences;
     c->have_sequences = false;
-    c->plan_valid = false;
-    c->cells_ref_valid = false;
-    std::string e = build_arena_layout(lens, n, dim, c->arena);
+    Arena next;
+    std::string e = build_arena_layout(lens, n, dim, next);
     if (!e.empty()) return fail(c, APD_ERR_INVALID, e);
+    // The unit plan and the reference cell count depend on the lengths only: a new batch
+    // with the same lengths (the usual case when a caller re-aligns re-encoded slices)
+    // keeps them and the uploaded unit list.
+    const bool same_layout = had && next.n == c->arena.n && next.dim == c->arena.dim && next.len == c->arena.len &&
+                             next.perm == c->arena.perm;
+    if (!same_layout) {
+        c->plan_valid = false;
+        c->cells_ref_valid = false;
+    }
+    c->arena = std::move(next);
     return ensure_device(c, c->d_arena, c->arena_cap, (size_t)c->arena.total_frames * c->arena.dpad);
 }
 
