@@ -58,7 +58,9 @@ class apd_stats(C.Structure):
                 ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64),
                 ("sm_clock_mhz", C.c_float),
-                ("sm_count", C.c_uint32)]
+                ("sm_count", C.c_uint32),
+                ("select_ms", C.c_float),
+                ("reserved", C.c_uint32)]
 
 
 # Every symbol include/apd.h declares: name -> (restype, argtypes).
@@ -83,6 +85,8 @@ PROTOTYPES = {
     "apd_align_pairs": (C.c_int, [C.c_void_p, _pp, _u32p, C.c_uint64, _fp, _u32p, C.c_uint64, _u64p]),
     "apd_align_pairs_band": (C.c_int, [C.c_void_p, _pp, C.c_uint64, _u32p, C.c_uint64, _fp, _u32p,
                                        C.c_uint64, _u64p]),
+    "apd_percentile_matrix": (C.c_int, [C.c_void_p, C.c_float, _fp]),
+    "apd_percentile_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, _fp]),
     "apd_get_stats": (C.c_int, [C.c_void_p, C.POINTER(apd_stats)]),
 }
 

@@ -179,6 +179,19 @@ class Context:
             return scores
         return scores, [paths[q, :min(int(lens[q]), cap)].copy() for q in range(k)], lens[:k].copy()
 
+    def percentile(self, perc):
+        """numerics::percentile (src/numerics.rs:125-133) of the matrix the last align_all left on
+        the device -- the clustering threshold of src/clustering.rs:101, without a host sort."""
+        out = C.c_float(0)
+        self._check(self._lib.apd_percentile_matrix(self._h, float(perc), C.byref(out)))
+        return np.float32(out.value)
+
+    def percentile_device(self, d_ptr, length, perc, stream=0):
+        out = C.c_float(0)
+        self._check(self._lib.apd_percentile_device(self._h, C.c_void_p(d_ptr), int(length), float(perc),
+                                                    C.c_void_p(stream), C.byref(out)))
+        return np.float32(out.value)
+
     def stats(self):
         s = apd_stats()
         self._check(self._lib.apd_get_stats(self._h, C.byref(s)))

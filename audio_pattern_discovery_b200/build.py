@@ -71,7 +71,7 @@ def build(force=False, verbose=False, ptxas_info=False):
         o = os.path.join(OBJ, "dtw_inst_%d.o" % d)
         objs.append(o)
         jobs.append([nvcc] + NVCC_FLAGS + extra + ["-DAPD_DPAD=%d" % d, "-c", "-o", o, os.path.join(CSRC, "dtw_inst.cu")])
-    for name in ("apd_api", "pair_path"):
+    for name in ("apd_api", "pair_path", "percentile"):
         o = os.path.join(OBJ, name + ".o")
         objs.append(o)
         jobs.append([nvcc] + NVCC_FLAGS + extra + ["-c", "-o", o, os.path.join(CSRC, name + ".cu")])

@@ -17,6 +17,7 @@
 #include "dtw_kernels.cuh"
 #include "host_plan.h"
 #include "pair_path.cuh"
+#include "percentile.cuh"
 
 using namespace apd;
 
@@ -55,6 +56,8 @@ struct apd_ctx {
     unsigned int* d_counters = nullptr;                 // one work counter per class
     int* d_error = nullptr;
     unsigned long long* d_tiles = nullptr;
+    unsigned long long* d_hist = nullptr;               // 256 radix-select counters
+    bool matrix_valid = false;                          // d_matrix holds the last apd_align_all result
 
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
     cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
@@ -186,6 +189,7 @@ apd_status begin_sequences(apd_ctx* c, const uint32_t* lens, uint32_t n, uint32_
     APD_CUDA(c, cudaSetDevice(c->device));
     const bool had = c->have_sequences;
     c->have_sequences = false;
+    c->matrix_valid = false;
     Arena next;
     std::string e = build_arena_layout(lens, n, dim, next);
     if (!e.empty()) return fail(c, APD_ERR_INVALID, e);
@@ -422,6 +426,7 @@ apd_status apd_create(int device_id, apd_ctx** out)
     APD_CREATE_CUDA(cudaMalloc((void**)&c->d_counters, 8 * sizeof(unsigned int)));
     APD_CREATE_CUDA(cudaMalloc((void**)&c->d_error, sizeof(int)));
     APD_CREATE_CUDA(cudaMalloc((void**)&c->d_tiles, sizeof(unsigned long long)));
+    APD_CREATE_CUDA(cudaMalloc((void**)&c->d_hist, 256 * sizeof(unsigned long long)));
     cudaEvent_t* evs[] = {&c->ev_k0, &c->ev_k1, &c->ev_s0, &c->ev_s1, &c->ev_h0, &c->ev_h1, &c->ev_d0, &c->ev_d1};
     for (cudaEvent_t* ev : evs) APD_CREATE_CUDA(cudaEventCreate(ev));
 #undef APD_CREATE_CUDA
@@ -437,7 +442,7 @@ void apd_destroy(apd_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void* dptrs[] = {c->d_arena, c->d_off, c->d_len, c->d_perm, c->d_srcoff, c->d_raw, c->d_units, c->d_packed,
-                     c->d_matrix, c->d_gstate, c->d_counters, c->d_error, c->d_tiles};
+                     c->d_matrix, c->d_gstate, c->d_counters, c->d_error, c->d_tiles, c->d_hist};
     for (void* p : dptrs) if (p) cudaFree(p);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     cudaEvent_t evs[] = {c->ev_k0, c->ev_k1, c->ev_s0, c->ev_s1, c->ev_h0, c->ev_h1, c->ev_d0, c->ev_d1};
@@ -592,7 +597,9 @@ apd_status apd_align_all(apd_ctx* c, const apd_params* p, float* out_nxn)
     APD_CUDA(c, cudaEventRecord(c->ev_d1, c->stream));
     c->timed_d2h = true;
     c->stats.d2h_bytes = N * N * sizeof(float);
-    return finish(c, c->stream);
+    s = finish(c, c->stream);
+    c->matrix_valid = (s == APD_OK);
+    return s;
 }
 
 static apd_status align_pairs_impl(apd_ctx* c, const apd_params* p, long long band_override, const uint32_t* pairs_ij,
@@ -636,6 +643,35 @@ apd_status apd_align_pair(apd_ctx* c, const apd_params* p, uint32_t i, uint32_t 
 {
     uint32_t pr[2] = {i, j};
     return apd_align_pairs(c, p, pr, 1, score, path_ij, path_cap, path_len);
+}
+
+static apd_status percentile_impl(apd_ctx* c, const float* d_x, uint64_t len, float perc, cudaStream_t st, float* out)
+{
+    if (!out) return fail(c, APD_ERR_INVALID, "out is NULL");
+    if (len == 0) return fail(c, APD_ERR_INVALID, "percentile of an empty slice: the reference panics (index out of bounds)");
+    std::string err;
+    uint64_t valid = 0;
+    cudaError_t e = percentile_select(d_x, len, perc, c->d_hist, c->sm_count, st, out, &valid, &c->stats.select_ms, err);
+    if (e != cudaSuccess) return fail(c, APD_ERR_CUDA, cudaGetErrorString(e));
+    if (!err.empty()) return fail(c, APD_ERR_INVALID, err);
+    return APD_OK;
+}
+
+apd_status apd_percentile_matrix(apd_ctx* c, float perc, float* out)
+{
+    if (!c) return APD_ERR_INVALID;
+    if (!c->matrix_valid) return fail(c, APD_ERR_STATE, "no matrix on the device: call apd_align_all first");
+    APD_CUDA(c, cudaSetDevice(c->device));
+    const uint64_t N = c->arena.n;
+    return percentile_impl(c, c->d_matrix, N * N, perc, c->stream, out);
+}
+
+apd_status apd_percentile_device(apd_ctx* c, const float* d_x, uint64_t len, float perc, void* stream, float* out)
+{
+    if (!c) return APD_ERR_INVALID;
+    if (!d_x && len) return fail(c, APD_ERR_INVALID, "d_x is NULL");
+    APD_CUDA(c, cudaSetDevice(c->device));
+    return percentile_impl(c, d_x, len, perc, stream ? (cudaStream_t)stream : c->stream, out);
 }
 
 apd_status apd_get_stats(apd_ctx* c, apd_stats* out)

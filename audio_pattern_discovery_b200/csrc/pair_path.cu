@@ -32,7 +32,7 @@ __device__ __forceinline__ float pair_distance(const float* __restrict__ x, cons
         }
         return __fsqrt_rn(acc);
     }
-    // Same association as frame_sqdist<.., false>: even / odd partial sums with FMAs.
+    // Same association as the FAST A stage of row_step(): even / odd partial sums with FMAs.
     float a0 = 0.0f, a1 = 0.0f;
     for (int k = 0; k < dpad; k += 2) {
         float d0 = x[k] - y[k], d1 = x[k + 1] - y[k + 1];

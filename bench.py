@@ -295,6 +295,18 @@ def run_b200(args):
     e2e_gcups = cells_total / (e2e_ms_step / 1e3) / 1e9
     h2d = al.stats()["h2d_bytes"]
 
+    # the threshold step of the handoff (src/clustering.rs:101) on the assembled device matrix
+    sel = None
+    if rank == 0:
+        m = al.align_all_device(c["pct"], ins, dele, mat)
+        al.synchronize()
+        thr = [al.ctx.percentile_device(m.data_ptr(), n * n, 0.05, al.stream.cuda_stream) for _ in range(3)][-1]
+        sel_ms = al.stats()["select_ms"]
+        sel = {"clustering_percentile": 0.05, "threshold": float(thr), "ms": sel_ms, "passes": 4,
+               "algorithmic_bytes": 16 * n * n, "achieved_gbs": 16 * n * n / (sel_ms / 1e3) / 1e9,
+               "peak_gbs": peaks.get("hbm_gbs"), "frac": 16 * n * n / (sel_ms / 1e3) / 1e9 / peaks.get("hbm_gbs", 6650.0)}
+    barrier()
+
     other = None
     if args.other_mode_steps > 0:
         omode = APD_MODE_FAST if strict else APD_MODE_STRICT
@@ -322,6 +334,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(n * n * 4), "steps": e2e_steps, "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches),
             "other_mode": other,
+            "threshold_select": sel,
             "clocks": clocks,
             "roofline": {
                 "bound": "fp32-issue", "kernel": "dtw_units_kernel (%s)" % args.mode,

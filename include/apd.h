@@ -69,6 +69,8 @@ typedef struct {
     uint64_t h2d_bytes, d2h_bytes;
     float sm_clock_mhz;          /* clock rate the device reports (max), for rooflines */
     uint32_t sm_count;
+    float select_ms;             /* radix-select passes of the last apd_percentile_* call */
+    uint32_t reserved;
 } apd_stats;
 
 /* ---- lifecycle ------------------------------------------------------------ */
@@ -148,6 +150,20 @@ apd_status apd_align_pairs(apd_ctx *ctx, const apd_params *p, const uint32_t *pa
 apd_status apd_align_pairs_band(apd_ctx *ctx, const apd_params *p, uint64_t warping_band,
                                 const uint32_t *pairs_ij, uint64_t n_pairs, float *scores,
                                 uint32_t *paths_ij, uint64_t path_cap, uint64_t *path_lens);
+
+/* ---- threshold for the handoff to clustering ---------------------------------- */
+
+/* Replaces numerics::percentile (src/numerics.rs:125-133) as AgglomerativeClustering::clustering
+ * calls it on the whole matrix (src/clustering.rs:101): the element at index
+ * (len as f32 * perc) as usize of the ascending non-NaN entries -- NaNs are dropped but the
+ * index comes from the unfiltered length, +INF and the diagonal zeros take part.  An index
+ * past the filtered length is the reference's out-of-bounds panic: APD_ERR_INVALID.
+ * apd_percentile_matrix works on the device copy of the matrix the last apd_align_all left
+ * behind; apd_percentile_device on any 16-byte-aligned device buffer (e.g. the matrix
+ * apd_scatter_packed wrote), enqueued on `stream` and synchronised before returning. */
+apd_status apd_percentile_matrix(apd_ctx *ctx, float perc, float *out);
+apd_status apd_percentile_device(apd_ctx *ctx, const float *d_x, uint64_t len, float perc,
+                                 void *stream, float *out);
 
 /* ---- introspection --------------------------------------------------------- */
 apd_status apd_get_stats(apd_ctx *ctx, apd_stats *out);

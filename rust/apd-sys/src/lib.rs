@@ -42,6 +42,8 @@ pub struct apd_stats {
     pub d2h_bytes: u64,
     pub sm_clock_mhz: f32,
     pub sm_count: u32,
+    pub select_ms: f32,
+    pub reserved: u32,
 }
 
 extern "C" {
@@ -66,5 +68,8 @@ extern "C" {
     pub fn apd_align_pairs_band(ctx: *mut apd_ctx, p: *const apd_params, warping_band: u64, pairs_ij: *const u32,
                                 n_pairs: u64, scores: *mut f32, paths_ij: *mut u32, path_cap: u64,
                                 path_lens: *mut u64) -> c_int;
+    pub fn apd_percentile_matrix(ctx: *mut apd_ctx, perc: f32, out: *mut f32) -> c_int;
+    pub fn apd_percentile_device(ctx: *mut apd_ctx, d_x: *const f32, len: u64, perc: f32, stream: *mut c_void,
+                                 out: *mut f32) -> c_int;
     pub fn apd_get_stats(ctx: *mut apd_ctx, out: *mut apd_stats) -> c_int;
 }

@@ -33,7 +33,7 @@ def test_abi_version(apd_lib_path):
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_capi.apd_params) == 20
-    assert C.sizeof(_capi.apd_stats) == 8 * 6 + 4 * 5 + 4 + 8 * 2 + 4 + 4  # incl. padding before h2d_bytes
+    assert C.sizeof(_capi.apd_stats) == 8 * 6 + 4 * 5 + 4 + 8 * 2 + 4 + 4 + 4 + 4  # incl. padding before h2d_bytes
 
 
 def test_no_cpu_path_without_device(apd_lib_path):

@@ -355,3 +355,48 @@ def test_full_c3_matrix_spot_check_and_properties():
     pairs = pairs[pairs[:, 0] != pairs[:, 1]]
     want = oracle.align_pairs(seqs, pairs, c["pct"], *c["weights"], workers=8)
     assert np.array_equal(bits(strict[pairs[:, 0], pairs[:, 1]]), bits(want))
+
+
+def test_device_percentile_matches_reference_quirks():
+    """numerics::percentile (src/numerics.rs:125-133) as an exact device order statistic."""
+    import torch
+    from audio_pattern_discovery_b200 import ApdError, Context
+    rng = np.random.default_rng(23)
+    with Context(0) as c:
+        for trial in range(12):
+            n = int(rng.integers(1, 200000))
+            x = rng.normal(size=n).astype(np.float32)
+            if trial % 3 == 0:
+                x[rng.integers(0, n, size=max(1, n // 50))] = np.nan     # dropped, index from unfiltered length
+            if trial % 4 == 1:
+                x[rng.integers(0, n, size=max(1, n // 20))] = np.inf
+                x[rng.integers(0, n, size=max(1, n // 20))] = 0.0
+            if trial % 5 == 2:
+                x = np.abs(x)
+            t = torch.from_numpy(x).cuda()
+            for perc in (0.0, 0.05, 0.5, 0.9):
+                try:
+                    want = oracle.percentile(x, perc)
+                except IndexError:
+                    with pytest.raises(ApdError):
+                        c.percentile_device(t.data_ptr(), n, perc)
+                    continue
+                got = c.percentile_device(t.data_ptr(), n, perc)
+                assert bits(got)[0] == bits(want)[0] or (got == 0 and want == 0), (trial, perc, got, want)
+        t = torch.arange(10, dtype=torch.float32, device="cuda")
+        with pytest.raises(ApdError):                      # index == len: the reference panics
+            c.percentile_device(t.data_ptr(), 10, 1.0)
+        with pytest.raises(ApdError):
+            c.percentile(0.5)                              # no matrix yet
+
+
+def test_threshold_of_the_device_matrix_equals_host_percentile():
+    from audio_pattern_discovery_b200 import Context, synth
+    seqs, _ = synth.make_sequences(300, np.random.default_rng(24).integers(20, 80, size=300), 10, 9, 24)
+    seqs[5] = np.ones((1, 10), np.float32)   # 1-frame sequence: +INF rows / columns take part in the sort
+    with Context(0) as c:
+        c.set_sequences(seqs)
+        m = c.align_all(0.1)
+        for perc in (0.05, 0.25, 0.999):
+            assert bits(c.percentile(perc))[0] == bits(oracle.percentile(m, perc))[0]
+        assert c.stats()["select_ms"] > 0
