@@ -9,3 +9,4 @@ from .alignments import (APD_MODE_FAST, APD_MODE_STRICT, Alignment, AlignmentPar
                          AlignmentWorkers, ApdError, Context)
 from .discovery import Discovery  # noqa: F401
 from .spectrogram import NDSequence  # noqa: F401
+from .clustering import AgglomerativeClustering, ClusteringOperation, Merge  # noqa: F401,E402

@@ -63,6 +63,11 @@ class apd_stats(C.Structure):
                 ("reserved", C.c_uint32)]
 
 
+class apd_merge(C.Structure):
+    _fields_ = [("merge_i", C.c_uint32), ("merge_j", C.c_uint32), ("into", C.c_uint32),
+                ("distance", C.c_float), ("operation", C.c_uint32), ("tie", C.c_uint32)]
+
+
 # Every symbol include/apd.h declares: name -> (restype, argtypes).
 _fp = C.POINTER(C.c_float)
 _u32p = C.POINTER(C.c_uint32)
@@ -87,6 +92,7 @@ PROTOTYPES = {
                                        C.c_uint64, _u64p]),
     "apd_percentile_matrix": (C.c_int, [C.c_void_p, C.c_float, _fp]),
     "apd_percentile_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, _fp]),
+    "apd_upgma": (C.c_int, [_fp, C.c_uint32, C.c_float, _fp, C.POINTER(apd_merge), _u32p, _fp, _u32p]),
     "apd_get_stats": (C.c_int, [C.c_void_p, C.POINTER(apd_stats)]),
 }
 

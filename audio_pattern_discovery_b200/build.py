@@ -75,9 +75,10 @@ def build(force=False, verbose=False, ptxas_info=False):
         o = os.path.join(OBJ, name + ".o")
         objs.append(o)
         jobs.append([nvcc] + NVCC_FLAGS + extra + ["-c", "-o", o, os.path.join(CSRC, name + ".cu")])
-    o = os.path.join(OBJ, "host_plan.o")
-    objs.append(o)
-    jobs.append(["g++"] + CXX_FLAGS + ["-c", "-o", o, os.path.join(CSRC, "host_plan.cpp")])
+    for name in ("host_plan", "upgma"):
+        o = os.path.join(OBJ, name + ".o")
+        objs.append(o)
+        jobs.append(["g++"] + CXX_FLAGS + ["-c", "-o", o, os.path.join(CSRC, name + ".cpp")])
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         list(ex.map(lambda c: _run(c, verbose), jobs))
     _run([nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-Xcompiler", "-fPIC", "-cudart", "static"], verbose)

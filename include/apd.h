@@ -165,6 +165,31 @@ apd_status apd_percentile_matrix(apd_ctx *ctx, float perc, float *out);
 apd_status apd_percentile_device(apd_ctx *ctx, const float *d_x, uint64_t len, float perc,
                                  void *stream, float *out);
 
+/* ---- clustering on the host (the consumer of the matrix) ------------------------ */
+
+/* src/clustering.rs:18-25 (ClusteringOperation) */
+typedef struct {
+    uint32_t merge_i, merge_j, into;
+    float distance;
+    uint32_t operation; /* src/clustering.rs:7-13: 0 Sequence2Sequence, 1 Sequence2Cluster,
+                           2 Cluster2Sequence, 3 Cluster2Cluster */
+    uint32_t tie;       /* 1 if another unordered root pair had exactly the same linkage (the
+                           reference's choice then depends on HashSet iteration order) */
+} apd_merge;
+
+/* A result-identical fast form of AgglomerativeClustering::clustering (src/clustering.rs:81-110
+ * with merge/linkage 153-209): same f32 linkage values (x-major sums recomputed only for the
+ * merged cluster), strict-`<` argmin over roots in ascending id, the reference's stop rule
+ * (`while n_clusters > 1 && distance < threshold`, so the merge that reaches the threshold is
+ * still applied).  HOST code and host buffers: dist_nxn is the n*n row-major matrix, ops holds
+ * n-1 entries, assignment (n entries, may be NULL) receives each instance's final root.
+ * threshold_in == NULL: the threshold is numerics::percentile(dist, perc) computed here;
+ * otherwise *threshold_in is used (e.g. from apd_percentile_matrix).  Returns APD_ERR_INVALID
+ * where the reference panics (percentile index out of bounds). */
+apd_status apd_upgma(const float *dist_nxn, uint32_t n, float perc, const float *threshold_in,
+                     apd_merge *ops, uint32_t *n_ops, float *threshold_out,
+                     uint32_t *assignment_out);
+
 /* ---- introspection --------------------------------------------------------- */
 apd_status apd_get_stats(apd_ctx *ctx, apd_stats *out);
 

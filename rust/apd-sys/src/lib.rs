@@ -46,6 +46,17 @@ pub struct apd_stats {
     pub reserved: u32,
 }
 
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct apd_merge {
+    pub merge_i: u32,
+    pub merge_j: u32,
+    pub into: u32,
+    pub distance: f32,
+    pub operation: u32,
+    pub tie: u32,
+}
+
 extern "C" {
     pub fn apd_abi_version() -> u32;
     pub fn apd_create(device_id: c_int, out: *mut *mut apd_ctx) -> c_int;
@@ -71,5 +82,7 @@ extern "C" {
     pub fn apd_percentile_matrix(ctx: *mut apd_ctx, perc: f32, out: *mut f32) -> c_int;
     pub fn apd_percentile_device(ctx: *mut apd_ctx, d_x: *const f32, len: u64, perc: f32, stream: *mut c_void,
                                  out: *mut f32) -> c_int;
+    pub fn apd_upgma(dist_nxn: *const f32, n: u32, perc: f32, threshold_in: *const f32, ops: *mut apd_merge,
+                     n_ops: *mut u32, threshold_out: *mut f32, assignment_out: *mut u32) -> c_int;
     pub fn apd_get_stats(ctx: *mut apd_ctx, out: *mut apd_stats) -> c_int;
 }
