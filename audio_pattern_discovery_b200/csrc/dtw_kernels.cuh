@@ -7,9 +7,10 @@
 //
 // Data layout (see host_plan.h): one arena of zero-padded DPAD-float frames, every
 // frame 16-byte aligned, sequences sorted by length.  Per warp in shared memory:
-//   xs   : 3 x (4 frames x DPAD floats)  stage of the shared row sequence x, two tiles
-//          ahead of the recurrence (coalesced LDG.128 by lanes < DPAD -> STS.128, read
-//          back as warp-broadcast LDS.128)
+//   xs   : 4 x (4 frames x DPAD floats)  stage of the shared row sequence x, three tiles
+//          ahead of the recurrence: asynchronous 16-byte copies (cp.async -> LDGSTS), one
+//          group per tile, read back as warp-broadcast LDS.128 (a TMA bulk-copy variant is
+//          kept behind APD_X_STAGE_TMA; it measured slower)
 //   ring : St tiles x 2 halves x 32 lanes x float4 -- boundary column of the previous
 //          column block ((D1, D2) of 2 rows per float4), lane-contiguous so LDS.128 /
 //          STS.128 are conflict-free.
@@ -25,6 +26,10 @@
 //                512-byte rows, L2 resident); bands too tall for shared memory.
 #pragma once
 #include <cuda_runtime.h>
+
+#ifndef APD_X_STAGE_TMA
+#define APD_X_STAGE_TMA 0  // 1: stage x rows with cp.async.bulk + mbarrier (measured slower, see DevCtx::x_fetch)
+#endif
 #include <stdint.h>
 
 #include "dtw_core.h"
@@ -53,7 +58,7 @@ struct KernelArgs {
 
 #if defined(__CUDACC__)
 
-enum { X_STAGES = 3 };  // x row-tile stage buffers per warp
+enum { X_BAR_F4 = 2 };  // float4 slots holding the X_STAGES mbarriers behind the stage buffers
 enum { RING_SMEM = 0, RING_GLOBAL = 1, RING_TMEM = 2 };
 enum { TMEM_WARPS = 4, TMEM_COLS = 256, TMEM_RING_TILES = TMEM_COLS / 8 };
 
@@ -65,10 +70,13 @@ struct DevCtx {
     const float4* xbase4;  // frame 0 of x
     const float4* ybase4;  // frame 0 of this lane's y
     float4* xs4;           // X_STAGES x DPAD float4
+    uint32_t xs_smem;      // shared-space address of xs4
+    uint32_t bar_smem;     // shared-space address of the X_STAGES mbarriers (8 bytes each)
+    uint32_t phase;        // bit b: parity the next wait on buffer b expects
+    uint32_t pending;      // bit b: a bulk copy into buffer b has not been awaited yet
     float4* ring4;         // this lane's ring column: tile s, half h at ring4[(2 * s + h) * 32]
     int St;                // ring size in tiles
     uint32_t taddr;        // RING_TMEM: (first lane of the warp's quadrant << 16) | first column
-    float4 xreg;
     unsigned int tiles;
 
     APD_D void sweep_info(int J, int& Ilo, int& Ihi, int& Nlo, int& Nhi) const
@@ -85,19 +93,95 @@ struct DevCtx {
     {
         return xbase4 + (ptrdiff_t)(4 * I - rg.rho - 1) * (DPAD / 4) + lane;
     }
+#if APD_X_STAGE_TMA
+    // EXPERIMENT (-DAPD_X_STAGE_TMA=1): x rows staged with the TMA unit's 1-D bulk copy
+    // (cp.async.bulk, SASS UBLKCP): one elected lane arms the buffer's mbarrier with the byte
+    // count and issues the copy of the tile's 4 contiguous frames; readers wait on the phase
+    // parity.  Correct (GPU parity suite green) but measured SLOWER on the headline workload:
+    // 1073 -> 944 GCUPS (FAST), 729 -> 610 (STRICT) at C3/n=2000 with 2- and 3-tile lookahead
+    // alike -- the ~90-cycle mbarrier.try_wait round trip (B300_MICROARCH: TRYWAIT 90 when
+    // already complete) is exposed once per tile by in-order issue, and the bulk copy bypasses
+    // L1 where re-read x rows otherwise hit.  Kept for reference; the default is cp.async below.
+    APD_D void x_fetch(int I, int buf, bool valid)
+    {
+        __syncwarp();
+        if (valid && lane == 0) {
+            const uint32_t bar = bar_smem + 8u * (uint32_t)buf;
+            const uint32_t dst = xs_smem + (uint32_t)(buf * DPAD * 16);
+            const float4* src = xbase4 + (ptrdiff_t)(4 * I - rg.rho - 1) * (DPAD / 4);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(DPAD * 16)));
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(src), "r"((uint32_t)(DPAD * 16)), "r"(bar));
+        }
+        if (valid) pending |= 1u << buf;
+    }
+    APD_D void x_wait(int buf)
+    {
+        if ((pending >> buf) & 1u) {
+            const uint32_t bar = bar_smem + 8u * (uint32_t)buf;
+            const uint32_t parity = (phase >> buf) & 1u;
+            asm volatile(
+                "{\n.reg .pred p;\n"
+                "WAIT_%=:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@!p bra WAIT_%=;\n}"
+                :
+                : "r"(bar), "r"(parity)
+                : "memory");
+            phase ^= 1u << buf;
+            pending &= ~(1u << buf);
+        }
+    }
     APD_D void x_preload(int buf, int I)
     {
-        __syncwarp();
-        if (lane < DPAD) xs4[buf * DPAD + lane] = __ldg(xaddr(I));
+        x_fetch(I, buf, true);
+        x_wait(buf);
+    }
+#else
+    // x rows are staged with asynchronous 16-byte copies (cp.async -> SASS LDGSTS): lanes
+    // < DPAD each move one float4 of the tile's 4 contiguous frames straight from L1/L2 into
+    // the stage buffer -- no staging register, no STS -- one committed group per pipeline step
+    // (an empty one when there is nothing left to fetch, so the group count stays in step).
+    // A tile's group was committed X_LOOK steps before its first read: wait_group X_LOOK-1.
+    APD_D void x_fetch(int I, int buf, bool valid)
+    {
+        if (valid && lane < DPAD) {
+            const uint32_t dst = xs_smem + (uint32_t)((buf * DPAD + lane) * 16);
+            const float4* src = xbase4 + (ptrdiff_t)(4 * I - rg.rho - 1) * (DPAD / 4) + lane;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+        }
+        asm volatile("cp.async.commit_group;");
+    }
+    APD_D void x_wait(int)
+    {
+        asm volatile("cp.async.wait_group %0;" ::"n"(X_LOOK - 1) : "memory");
+        __syncwarp();  // the other lanes' copies are visible, and nobody is still reading the
+                       // buffer the next x_fetch overwrites
+    }
+    APD_D void x_preload(int buf, int I)
+    {
+        x_fetch(I, buf, true);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
     }
-    APD_D void x_fetch(int I)
+#endif
+    APD_D void x_init()
     {
-        if (lane < DPAD) xreg = __ldg(xaddr(I));
-    }
-    APD_D void x_commit(int buf)
-    {
-        if (lane < DPAD) xs4[buf * DPAD + lane] = xreg;
+#if APD_X_STAGE_TMA
+        if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < X_STAGES; b++)
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_smem + 8u * (uint32_t)b) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+#endif
+        phase = 0;
+        pending = 0;
+        for (int k = lane; k < X_STAGES * DPAD; k += 32) xs4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#if APD_X_STAGE_TMA
+        // the zero fill (generic proxy) is ordered before later bulk copies (async proxy) into the same bytes
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
         __syncwarp();
     }
     APD_D void note_step(int) const {}
@@ -253,14 +337,15 @@ __global__ void __launch_bounds__(32) dtw_units_kernel(const KernelArgs a)
     DevCtx<DPAD, RING> ctx;
     ctx.lane = lane;
     ctx.xs4 = smem4;
+    ctx.xs_smem = (uint32_t)__cvta_generic_to_shared(smem4);
+    ctx.bar_smem = ctx.xs_smem + X_STAGES * DPAD * 16;
     float4* ring = (RING == RING_GLOBAL) ? reinterpret_cast<float4*>(a.gstate) + (size_t)blockIdx.x * ((size_t)a.St * 2 * 32)
-                                         : smem4 + X_STAGES * DPAD;
+                                         : smem4 + X_STAGES * DPAD + X_BAR_F4;
     ctx.ring4 = ring + lane;
     ctx.taddr = 0;
     ctx.St = a.St;
     ctx.tiles = 0;
-    for (int k = lane; k < X_STAGES * DPAD; k += 32) smem4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
+    ctx.x_init();
     warp_unit_loop<DPAD, STRICT, UNITW, RING>(a, ctx);
 }
 
@@ -285,13 +370,14 @@ __global__ void __launch_bounds__(32 * TMEM_WARPS, 2) dtw_units_tmem_kernel(cons
 
     DevCtx<DPAD, RING_TMEM> ctx;
     ctx.lane = lane;
-    ctx.xs4 = smem4 + warp * (X_STAGES * DPAD);
+    ctx.xs4 = smem4 + warp * (X_STAGES * DPAD + X_BAR_F4);
+    ctx.xs_smem = (uint32_t)__cvta_generic_to_shared(ctx.xs4);
+    ctx.bar_smem = ctx.xs_smem + X_STAGES * DPAD * 16;
     ctx.ring4 = nullptr;
     ctx.taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
     ctx.St = a.St;
     ctx.tiles = 0;
-    for (int k = lane; k < X_STAGES * DPAD; k += 32) ctx.xs4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
+    ctx.x_init();
     warp_unit_loop<DPAD, STRICT, UNITW, RING_TMEM>(a, ctx);
 
     asm volatile("tcgen05.fence::before_thread_sync;\n");
@@ -326,7 +412,7 @@ APD_DECLARE_DPAD(32)
 // Dynamic shared memory per CTA (one warp, or TMEM_WARPS warps for RING_TMEM).
 inline size_t dtw_smem_bytes(int dpad, int St, int ring)
 {
-    size_t x = (size_t)X_STAGES * 4 * dpad * sizeof(float);
+    size_t x = (size_t)X_STAGES * 4 * dpad * sizeof(float) + X_BAR_F4 * 16;
     if (ring == RING_TMEM) return x * TMEM_WARPS;
     return ring == RING_GLOBAL ? x : x + (size_t)St * TILE * 32 * sizeof(float2);
 }

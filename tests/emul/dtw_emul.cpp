@@ -50,8 +50,8 @@ struct HostCtx {
     const float* xaddr(int I) const { return xbase + (int64_t)(4 * I - rg.rho - 1) * DPAD; }
     void note_step(int kind) { if (lane == first_lane) steps[kind]++; }
     void x_preload(int buf, int I) { stage[buf] = xaddr(I); }
-    void x_fetch(int I) { fetched = xaddr(I); }
-    void x_commit(int buf) { stage[buf] = fetched; }
+    void x_fetch(int I, int buf, bool valid) { if (valid) stage[buf] = xaddr(I); }
+    void x_wait(int) const {}
     // the final pipeline step computes distances of stale rows (discarded): any readable memory will do
     const float* x_tile(int buf) const { return stage[buf] ? stage[buf] : xaddr(0); }
     void ring_load(int slot, F2 (&v)[TILE]) const { for (int r = 0; r < TILE; r++) v[r] = state[slot * TILE + r]; }
@@ -65,8 +65,7 @@ struct HostCtx {
         for (int c = 0; c < TILE; c++)
             for (int k = 0; k < DPAD / 2; k++) yv[c][k] = mk2(p[c * DPAD + 2 * k], p[c * DPAD + 2 * k + 1]);
     }
-    const float* stage[3] = {nullptr, nullptr, nullptr};
-    const float* fetched = nullptr;
+    const float* stage[X_STAGES] = {nullptr, nullptr, nullptr, nullptr};
     mutable bool mismatch = false;
     int first_lane = -1;
     uint64_t* steps = nullptr;
