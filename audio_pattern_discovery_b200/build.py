@@ -23,7 +23,7 @@ LIB = os.path.join(HERE, "libapd_b200.so")
 
 DPADS = (4, 8, 12, 16, 20, 24, 28, 32)
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ARCH + (["-DAPD_X_LOOK=%s" % os.environ["APD_X_LOOK"]] if os.environ.get("APD_X_LOOK") else []) + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fno-fast-math,-ffp-contract=off"]
+NVCC_FLAGS = ARCH + ["-D%s=%s" % (k, os.environ[k]) for k in ("APD_X_LOOK", "APD_USE_EDGE_VARIANT", "APD_X_STAGE_TMA") if os.environ.get(k)] + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fno-fast-math,-ffp-contract=off"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unknown-pragmas"]
 
 
