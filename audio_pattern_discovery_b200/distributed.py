@@ -72,6 +72,15 @@ class ShardedAligner:
     def synchronize(self):
         self.ctx.synchronize(self.stream.cuda_stream)
 
+    def percentile_of_matrix(self, perc):
+        """numerics::percentile of the assembled device matrix (local work, no collective)."""
+        m = self._matrix
+        return self.ctx.percentile_device(m.data_ptr(), m.numel(), perc, self.stream.cuda_stream)
+
+    def matrix_device(self):
+        """The matrix the last align_all_device / align_all assembled on this rank (no new work)."""
+        return self._matrix
+
     def stats(self):
         return self.ctx.stats()
 

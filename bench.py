@@ -31,6 +31,8 @@ if ROOT not in sys.path:
 
 METRIC = "dtw_gcups"
 UNIT = "GCUPS"
+DEVICE = "cuda"   # tests/test_bench_flow.py drives the multi-rank control flow on CPU with a stub aligner
+PIN = True
 
 
 def load_peaks():
@@ -210,7 +212,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks, peaks_src = load_peaks()
 
@@ -221,11 +223,11 @@ def run_b200(args):
     n = len(seqs)
     arena_bytes = sum(len(s) for s in seqs) * c["dim"] * 4
     need_flush = arena_bytes <= 126e6
-    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda") if need_flush else None
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=DEVICE) if need_flush else None
 
     al = ShardedAligner(seqs, device=local, mode=mode)
     al.ctx.packed_len(c["pct"], mode)                # builds the unit plan
-    cells_local_t = torch.tensor([al.stats()["cells_reference"]], dtype=torch.int64, device="cuda")
+    cells_local_t = torch.tensor([al.stats()["cells_reference"]], dtype=torch.int64, device=DEVICE)
     if world > 1:
         dist.all_reduce(cells_local_t)
     cells_total = int(cells_local_t[0])              # reference visit rule, all ordered pairs (library-side count)
@@ -238,7 +240,7 @@ def run_b200(args):
     def maxrank(x):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64, device=DEVICE)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
@@ -276,7 +278,7 @@ def run_b200(args):
     dtw_launches = max(st["kernel_launches"] - 1, 1)
 
     # ---- end-to-end arm: host buffers in, host matrix out ---------------------
-    host_out = torch.empty((n, n), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+    host_out = torch.empty((n, n), dtype=torch.float32, pin_memory=PIN) if rank == 0 else None
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     e2e_ms = []
     for it in range(1 + e2e_steps):
@@ -296,11 +298,12 @@ def run_b200(args):
     h2d = al.stats()["h2d_bytes"]
 
     # the threshold step of the handoff (src/clustering.rs:101) on the assembled device matrix
+    # NOTE: rank 0 only, so NO collective may be called here -- the matrix is the one every rank
+    # assembled in the last end-to-end step.
     sel = None
     if rank == 0:
-        m = al.align_all_device(c["pct"], ins, dele, mat)
-        al.synchronize()
-        thr = [al.ctx.percentile_device(m.data_ptr(), n * n, 0.05, al.stream.cuda_stream) for _ in range(3)][-1]
+        m = al.matrix_device()
+        thr = [al.percentile_of_matrix(0.05) for _ in range(3)][-1]
         sel_ms = al.stats()["select_ms"]
         sel = {"clustering_percentile": 0.05, "threshold": float(thr), "ms": sel_ms, "passes": 4,
                "algorithmic_bytes": 16 * n * n, "achieved_gbs": 16 * n * n / (sel_ms / 1e3) / 1e9,

@@ -33,3 +33,38 @@ def test_reference_arm_other_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        capture_output=True, text=True, timeout=120, env=env)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def _collective_calls_under_rank_branches(path):
+    """Every rank must issue the same sequence of collectives: a call that contains one (NCCL
+    all-gather inside align_all*, barrier, all_reduce, ...) inside an `if rank ...:` branch
+    deadlocks the other ranks.  Static check of the source."""
+    import ast
+    collectives = {"align_all_device", "align_all", "barrier", "maxrank", "all_reduce", "all_gather",
+                   "all_gather_into_tensor", "broadcast", "reduce_scatter", "measure_other_mode", "ShardedAligner",
+                   "init_process_group", "destroy_process_group"}
+    tree = ast.parse(open(path).read())
+    bad = []
+
+    def mentions_rank(node):
+        return any(isinstance(n, ast.Name) and n.id in ("rank", "local") or
+                   isinstance(n, ast.Attribute) and n.attr == "rank" for n in ast.walk(node))
+
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If) and mentions_rank(node.test):
+            for sub in node.body + node.orelse:
+                for call in ast.walk(sub):
+                    if isinstance(call, ast.Call):
+                        f = call.func
+                        name = f.attr if isinstance(f, ast.Attribute) else getattr(f, "id", None)
+                        on_oracle = isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) and f.value.id == "oracle"
+                        if name in collectives and not on_oracle:  # oracle.align_all is the CPU checker, not a collective
+                            bad.append((node.lineno, call.lineno, name))
+    return bad
+
+
+def test_no_collective_is_issued_by_a_subset_of_ranks():
+    for rel in ("bench.py", os.path.join("audio_pattern_discovery_b200", "distributed.py"),
+                os.path.join("tests", "multi_rank_check.py")):
+        bad = _collective_calls_under_rank_branches(os.path.join(ROOT, rel))
+        assert not bad, (rel, bad)
