@@ -266,8 +266,8 @@ float apd_oracle_dtw_dense(const float *x, uint64_t n, const float *y, uint64_t 
         uint64_t hi = i + w;
         if (hi < i) hi = UINT64_MAX;
         if (hi > m + 1) hi = m + 1;
-        /* cur currently holds row i-2: wipe the span it used */
-        for (uint64_t j = 0; j <= m + 1; j++) cur[j] = INFINITY;
+        /* cur still holds row i-2, but every read below is guarded by the span of the row it
+         * belongs to (prev_lo/prev_hi for row i-1, lo for this row), so nothing stale is read */
         for (uint64_t j = lo; j < hi; j++) {
             float distance = apd_oracle_euclidean(x + (i - 1) * dim, y + (j - 1) * dim, dim);
             float match_score = (j - 1 >= prev_lo && j - 1 < prev_hi) ? prev[j - 1] : INFINITY;
