@@ -352,6 +352,12 @@ def run_b200(args):
                                        / (kernel_ms_avg / 1e3) / (sm_count * 4 * 32 * peaks.get("sm_max_mhz", 1965.0) * 1e6),
                                    "note": "f32x2 ops occupy the 32-lane FMA pipe for 2 cycles (measured: "
                                            "profiles/r1_microbench*.txt); DESIGN.md section 4"},
+                "flops_view": {"algorithmic_flops_per_cell": 3 * c["dim"] + 7,
+                               "achieved_tflops": cells_local * (3 * c["dim"] + 7) / (kernel_ms_avg / 1e3) / 1e12,
+                               "peak_fp32_tflops": 2 * peak_max,
+                               "frac": cells_local * (3 * c["dim"] + 7) / (kernel_ms_avg / 1e3) / 1e12 / (2 * peak_max),
+                               "note": "3D+7 flops per ordered reference cell (SURVEY.md 8d) against the FP32 FMA peak "
+                                       "(2 flops per lane-instruction); subtractions, compares and the sqrt cannot be FMAs"},
                 "kernel_ms_per_step": kernel_ms_avg, "dtw_launches_per_step": dtw_launches,
                 "cells_per_step_this_gpu": int(cells_local), "scatter_ms_per_step": float(np.mean(scat_ms)),
                 "traffic": None,
