@@ -51,6 +51,19 @@ def test_cold_exact_path_schedule_matches_oracle():
         assert np.array_equal(bits(got), bits(want))
 
 
+@pytest.mark.parametrize("dim", [5, 13, 16, 24, 30, 32])
+def test_every_padded_frame_width(dim):
+    """One kernel instantiation per padded width 4..32: the quarter-points at which the
+    recurrence cells are interleaved with the distance work differ per width."""
+    rng = np.random.default_rng(100 + dim)
+    seqs = random_sequences(rng, 14, 6, 40, dim, integer=(dim % 2 == 1))
+    want = oracle.align_all(seqs, 0.2, 0.75, 0.5, 1.0, variant="dense")
+    got, _ = emul.align_all(seqs, 0.2, 0.75, 0.5, 1.0)
+    assert np.array_equal(bits(got), bits(want))
+    unit, _ = emul.align_all(seqs, 0.2)
+    assert np.array_equal(bits(unit), bits(oracle.align_all(seqs, 0.2, variant="dense")))
+
+
 def test_fast_mode_within_tolerance():
     rng = np.random.default_rng(3)
     seqs = random_sequences(rng, 20, 30, 80, 20, False)

@@ -400,3 +400,22 @@ def test_threshold_of_the_device_matrix_equals_host_percentile():
         for perc in (0.05, 0.25, 0.999):
             assert bits(c.percentile(perc))[0] == bits(oracle.percentile(m, perc))[0]
         assert c.stats()["select_ms"] > 0
+
+
+@pytest.mark.parametrize("dim", [5, 13, 16, 24, 30, 32])
+def test_every_padded_frame_width_on_gpu(dim):
+    rng = np.random.default_rng(100 + dim)
+    seqs = random_sequences(rng, 40, 6, 60, dim, integer=(dim % 2 == 1))
+    want = oracle.align_all(seqs, 0.2, 0.75, 0.5, 1.0, workers=8, variant="dense")
+    got, _ = gpu_matrix(seqs, 0.2, 0.75, 0.5, 1.0)
+    assert np.array_equal(bits(got), bits(want))
+    got, _ = gpu_matrix(seqs, 0.2)
+    assert np.array_equal(bits(got), bits(oracle.align_all(seqs, 0.2, workers=8, variant="dense")))
+
+
+def test_dim_above_the_supported_maximum_is_refused():
+    from audio_pattern_discovery_b200 import ApdError, Context
+    with Context(0) as c:
+        with pytest.raises(ApdError) as ei:
+            c.set_sequences([np.zeros((4, 33), np.float32)] * 2)
+        assert ei.value.status == 4  # APD_ERR_UNSUPPORTED
