@@ -60,3 +60,22 @@ def test_ndsequence_layout_contract():
     assert np.array_equal(s.vec(1), [4, 5, 6, 7])
     assert NDSequence(5, a).len() == 2  # ragged tail ignored (integer division)
     assert NDSequence.from_array(a.reshape(3, 4)).n_bins == 4
+
+
+def test_synthetic_workloads_are_deterministic_and_shaped():
+    """bench.py and the parity tests regenerate the BASELINE.json workloads from seeds on every box."""
+    from audio_pattern_discovery_b200 import synth
+    for name, n, dim in (("C2", 50, 20), ("C3", 20, 20), ("C4", 40, 8), ("C5", 2, 20)):
+        c1, a, la = synth.make_config(name, n)
+        c2, b, lb = synth.make_config(name, n)
+        assert len(a) == n and all(x.dtype == np.float32 and x.shape[1] == dim for x in a)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)) and np.array_equal(la, lb)
+        assert c1["pct"] == c2["pct"]
+    c, seqs, _ = synth.make_config("C2", 300)
+    lens = np.array([len(s) for s in seqs])
+    assert lens.min() >= 64 and lens.max() <= 256 and c["weights"] == (0.75, 0.5, 1.0)
+    c, seqs, _ = synth.make_config("C4", 300)
+    lens = np.array([len(s) for s in seqs])
+    assert lens.min() >= 97 and lens.max() <= 1024 and c["pct"] == 0.05
+    assert all(len(s) == 512 for s in synth.make_config("C3", 5)[1])
+    assert all(len(s) == 4096 for s in synth.make_config("C5", 2)[1])
