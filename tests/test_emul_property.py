@@ -1,0 +1,47 @@
+"""Property-based sweep of the kernel's lane program (host emulator) against the oracle: random
+sequence counts, lengths (incl. 0, 1, 2 frames), widths, band percentages (incl. 0, > 1, NaN),
+penalties and tie-heavy integer frames.  Every drawn case must match bit for bit."""
+import numpy as np
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from oracle import oracle
+
+from . import emul
+
+
+@st.composite
+def workloads(draw):
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    n = draw(st.integers(2, 40))
+    dim = draw(st.sampled_from([1, 2, 3, 4, 7, 10, 12, 20, 26]))
+    hi = draw(st.sampled_from([3, 9, 24, 70]))
+    integer = draw(st.booleans())
+    lens = rng.integers(0 if draw(st.booleans()) else 1, hi + 1, size=n)
+    seqs = []
+    for t in lens:
+        if integer:
+            seqs.append(rng.integers(0, 3, size=(int(t), dim)).astype(np.float32))
+        else:
+            seqs.append(rng.normal(size=(int(t), dim)).astype(np.float32))
+    if draw(st.booleans()) and n >= 3:
+        seqs[2] = seqs[0].copy()          # duplicates: zero distances on the hot path's sqrt
+    pct = draw(st.sampled_from([0.0, 0.03, 0.1, 0.25, 0.5, 1.0, 1.7, float("nan")]))
+    pens = draw(st.sampled_from([(1.0, 1.0, 1.0), (0.75, 0.5, 1.0), (0.5, 1.0, 0.25), (1.0, 0.0, 1.0), (0.3, 0.3, 0.3)]))
+    return seqs, pct, pens
+
+
+@settings(max_examples=70, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+@given(workloads())
+def test_lane_program_matches_oracle(case):
+    seqs, pct, (ins, dele, mat) = case
+    want = oracle.align_all(seqs, pct, ins, dele, mat, workers=2, variant="dense")
+    got, info = emul.align_all(seqs, pct, ins, dele, mat, strict=True)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # the shards of a 3-rank run tile the same matrix
+    acc = np.zeros_like(got)
+    for r in range(3):
+        part, _ = emul.align_all(seqs, pct, ins, dele, mat, strict=True, rank=r, world=3)
+        acc += part
+    assert np.array_equal(acc.view(np.uint32), want.view(np.uint32))
