@@ -65,6 +65,41 @@ def reference_cells_total(seqs, pct):
     return total
 
 
+def _band_sum(a, b, k):
+    """sum_{t=0}^{k-1} max(0, min(a, b - t))"""
+    if a <= 0 or b <= 0 or k <= 0:
+        return 0
+    k1 = min(max(b - a + 1, 0), k)
+    k2 = min(b, k)
+    s = a * k1
+    if k2 > k1:
+        s += (k2 - k1) * b - (k1 + k2 - 1) * (k2 - k1) // 2
+    return s
+
+
+def cells_visited(n, m, w):
+    """Closed form of SURVEY.md Appendix C (src/alignments.rs:174-175): diagonals j-i = 0..w-1 hold
+    min(n, m-k) cells, diagonals j-i = -1..-w hold min(m, n-k)."""
+    return _band_sum(n, m, w) + _band_sum(m, n - 1, w)
+
+
+def needed_cells_total(seqs, pct):
+    """The cells that can influence the score (rows <= n-1, columns <= m-1), all ordered pairs --
+    printed beside the reference's own count so the two GCUPS conventions convert."""
+    lens = np.array([len(s) for s in seqs])
+    vals, counts = np.unique(lens, return_counts=True)
+    total = 0
+    for a, ca in zip(vals, counts):
+        for b, cb in zip(vals, counts):
+            pairs = int(ca) * int(cb) - (int(ca) if a == b else 0)
+            if pairs and a >= 1 and b >= 1:
+                prod = float(np.float32(pct) * np.float32(max(a, b)))
+                band = 0 if (prod != prod or prod <= 0) else int(min(prod, 1e9))
+                w = max(band, abs(int(a) - int(b))) + 2
+                total += pairs * cells_visited(int(a) - 1, int(b) - 1, w)
+    return total
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -332,7 +367,8 @@ def run_b200(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, c, seqs),
             "matrix_wall_s": ms_per_step / 1e3, "matrix_wall_s_e2e": e2e_ms_step / 1e3,
-            "reference_cells": cells_total, "wall_s_timed_region": wall,
+            "reference_cells": cells_total, "needed_cells": needed_cells_total(seqs, c["pct"]),
+            "wall_s_timed_region": wall,
             "e2e": {"value": e2e_gcups, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(n * n * 4), "steps": e2e_steps, "ms_per_step": e2e_ms_step},
             "gpu_launches": int(launches),
