@@ -33,6 +33,9 @@ def lib():
         L.apd_emul_align_all.argtypes = [C.POINTER(fp), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32,
                                          C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                          C.c_uint32, C.c_uint32, fp, C.POINTER(C.c_uint64)]
+        L.apd_emul_plan_info.restype = C.c_int
+        L.apd_emul_plan_info.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_float, C.c_uint32,
+                                         C.c_uint32, C.POINTER(C.c_uint64)]
         L.apd_emul_cells_visited.restype = C.c_uint64
         L.apd_emul_cells_visited.argtypes = [C.c_uint64] * 3
         L.apd_emul_window.restype = C.c_int
@@ -59,3 +62,13 @@ def align_all(seqs, pct, ins=1.0, dele=1.0, mat=1.0, strict=True, rank=0, world=
     if rc:
         raise RuntimeError("emulator failed: %d" % rc)
     return out, info
+
+
+def plan_info(lens, dim, pct, rank=0, world=1):
+    lens = np.ascontiguousarray(lens, dtype=np.uint32)
+    info = np.zeros(16, dtype=np.uint64)
+    rc = lib().apd_emul_plan_info(lens.ctypes.data_as(C.POINTER(C.c_uint32)), len(lens), dim, pct, rank, world,
+                                  info.ctypes.data_as(C.POINTER(C.c_uint64)))
+    if rc:
+        raise RuntimeError("planner check failed: %d" % rc)
+    return info

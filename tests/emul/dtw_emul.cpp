@@ -7,6 +7,7 @@
 // masks, the boundary ring and the planner against the oracle without a GPU.  It is
 // NOT a fallback: nothing in the package loads it.
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -190,6 +191,37 @@ int apd_emul_align_all(const float* const* frames, const uint32_t* lens, uint32_
         }
     }
     return rc;
+}
+
+// Planner only (no DP): info[0] units, [1] classes, [2] reference cells of shard (rank, world),
+// [3] sum of the planner's tile estimates, [4..7] St per class, [8..11] gstate per class,
+// [12..15] units per class.
+int apd_emul_plan_info(const uint32_t* lens, uint32_t n, uint32_t dim, float pct, uint32_t rank, uint32_t world,
+                       uint64_t* info)
+{
+    Arena ar;
+    std::string err = build_arena_layout(lens, n, dim, ar);
+    if (!err.empty()) return -1;
+    UnitPlan plan;
+    build_unit_plan(ar, pct, plan);
+    std::memset(info, 0, 16 * sizeof(uint64_t));
+    info[0] = plan.units.size();
+    info[1] = plan.classes.size();
+    info[2] = reference_cells(ar, plan, rank, world);
+    info[3] = plan.tiles_estimate;
+    for (size_t c = 0; c < plan.classes.size() && c < 4; c++) {
+        info[4 + c] = (uint64_t)plan.classes[c].St;
+        info[8 + c] = plan.classes[c].gstate ? 1 : 0;
+        info[12 + c] = plan.classes[c].end - plan.classes[c].begin;
+    }
+    // every unordered pair appears in exactly one unit
+    uint64_t pairs = 0;
+    for (const Unit& u : plan.units) {
+        uint32_t b0 = std::max(32 * u.B, u.a + 1), b1 = std::min(32 * u.B + 32, n);
+        if (b1 > b0) pairs += b1 - b0;
+    }
+    if (pairs != (uint64_t)n * (n - 1) / 2) return -2;
+    return 0;
 }
 
 uint64_t apd_emul_cells_visited(uint64_t n, uint64_t m, uint64_t w) { return cells_visited(n, m, w); }

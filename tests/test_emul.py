@@ -121,3 +121,33 @@ def test_cells_visited_closed_form():
     for pct, n, m in [(0.1, 512, 512), (0.05, 1024, 128), (1.0, 4096, 4096), (0.0, 9, 4), (float("nan"), 5, 5)]:
         want = oracle.window(oracle.warping_band(pct, max(n, m)), n, m)
         assert L.apd_emul_window(pct, n, m) == min(want, n + m + 8)
+
+
+@pytest.mark.parametrize("name", ["C2", "C3", "C4", "C5"])
+def test_planner_at_full_baseline_sizes(name):
+    """The host planner on the full BASELINE.json shapes (lengths only, no DP): every unordered pair
+    in exactly one unit, the reference cell count equals the closed form summed in Python, the
+    shards of 8 ranks add up, and the launch classes are the expected ring homes."""
+    import time
+
+    import bench
+    from audio_pattern_discovery_b200 import synth
+    c = synth.config(name)
+    lens = np.full(c["n"], c["lens"]) if np.isscalar(c["lens"]) else np.asarray(c["lens"])
+    t0 = time.perf_counter()
+    info = emul.plan_info(lens, c["dim"], c["pct"])
+    assert time.perf_counter() - t0 < 30
+    vals, counts = np.unique(lens, return_counts=True)
+    want = 0
+    for a, ca in zip(vals, counts):
+        for b, cb in zip(vals, counts):
+            pairs = int(ca) * int(cb) - (int(ca) if a == b else 0)
+            w = oracle.window(oracle.warping_band(c["pct"], int(max(a, b))), int(a), int(b))
+            want += pairs * bench.cells_visited(int(a), int(b), w)
+    assert int(info[2]) == want
+    assert sum(int(emul.plan_info(lens, c["dim"], c["pct"], r, 8)[2]) for r in range(8)) == want
+    if name == "C3":
+        assert int(info[1]) == 1 and int(info[4]) <= 32 and int(info[8]) == 0   # one class, ring fits TMEM
+        assert want == 10000 * 9999 * 51463
+    if name == "C5":
+        assert int(info[8]) == 1                                                 # unbanded 4096: global ring
