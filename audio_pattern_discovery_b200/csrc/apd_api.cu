@@ -21,6 +21,11 @@
 
 using namespace apd;
 
+// The layouts the ctypes / Rust / C++ bindings mirror (tests/test_abi.py checks the Python side).
+static_assert(sizeof(apd_params) == 20, "apd_params layout is part of the ABI");
+static_assert(sizeof(apd_stats) == 104, "apd_stats layout is part of the ABI");
+static_assert(sizeof(apd_merge) == 24, "apd_merge layout is part of the ABI");
+
 namespace {
 
 thread_local std::string g_create_error;
