@@ -96,7 +96,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, workload="C3"):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
                       MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
@@ -110,18 +110,19 @@ def _worker(rank, world, port, q):
     torch.cuda.synchronize = lambda *a, **k: None
     torch.cuda.Event = _FakeEvent
     bench.emit = lambda line: q.put(json.dumps(line))
-    sys.argv = ["bench.py", "--gpus", str(world), "--seqs", "24", "--steps", "2", "--warmup", "1", "--no-cpu"]
+    sys.argv = ["bench.py", "--gpus", str(world), "--seqs", "24", "--steps", "2", "--warmup", "1", "--no-cpu",
+                "--workload", workload]
     # bench.main() destroys the process group itself
     rc = bench.main()
     q.put("rank%d rc=%s" % (rank, rc))
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_all_ranks_walk_the_same_collectives(world):
+@pytest.mark.parametrize("world,workload", [(2, "C3"), (3, "C3"), (2, "C2")])
+def test_all_ranks_walk_the_same_collectives(world, workload):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, workload)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
