@@ -23,7 +23,9 @@ APD_ERR_INTERNAL = 6
 APD_MODE_STRICT = 0
 APD_MODE_FAST = 1
 APD_MAX_DIM = 32
-APD_ABI_VERSION = 1
+APD_ABI_VERSION = 2
+APD_MAX_DEVICES = 8
+APD_AE_MAX_BINS = 64
 
 STATUS_NAMES = {0: "APD_OK", 1: "APD_ERR_INVALID", 2: "APD_ERR_NO_DEVICE", 3: "APD_ERR_CUDA",
                 4: "APD_ERR_UNSUPPORTED", 5: "APD_ERR_STATE", 6: "APD_ERR_INTERNAL"}
@@ -60,7 +62,7 @@ class apd_stats(C.Structure):
                 ("sm_clock_mhz", C.c_float),
                 ("sm_count", C.c_uint32),
                 ("select_ms", C.c_float),
-                ("reserved", C.c_uint32)]
+                ("path_ms", C.c_float)]
 
 
 class apd_merge(C.Structure):
@@ -76,10 +78,16 @@ _pp = C.POINTER(apd_params)
 PROTOTYPES = {
     "apd_abi_version": (C.c_uint32, []),
     "apd_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "apd_create_multi": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "apd_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "apd_group_size": (C.c_int, [C.c_void_p, _u32p, _u32p]),
     "apd_destroy": (None, [C.c_void_p]),
     "apd_last_error": (C.c_char_p, [C.c_void_p]),
     "apd_set_sequences": (C.c_int, [C.c_void_p, C.POINTER(_fp), _u32p, C.c_uint32, C.c_uint32]),
     "apd_set_sequences_flat": (C.c_int, [C.c_void_p, C.c_void_p, _u64p, _u32p, C.c_uint32, C.c_uint32]),
+    "apd_set_sequences_encoded": (C.c_int, [C.c_void_p, C.POINTER(_fp), _u32p, C.c_uint32, C.c_uint32, _fp, _fp,
+                                           C.c_uint32]),
+    "apd_get_sequence": (C.c_int, [C.c_void_p, C.c_uint32, _fp, C.c_uint64]),
     "apd_set_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "apd_align_all": (C.c_int, [C.c_void_p, _pp, C.c_void_p]),
     "apd_packed_len": (C.c_int, [C.c_void_p, _pp, _u64p]),
@@ -94,6 +102,11 @@ PROTOTYPES = {
     "apd_percentile_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_float, C.c_void_p, _fp]),
     "apd_upgma": (C.c_int, [_fp, C.c_uint32, C.c_float, _fp, C.POINTER(apd_merge), _u32p, _fp, _u32p]),
     "apd_get_stats": (C.c_int, [C.c_void_p, C.POINTER(apd_stats)]),
+    "apd_last_launch_plan": (C.c_char_p, [C.c_void_p]),
+    "apd_save_matrix": (C.c_int, [C.c_char_p, _fp, C.c_uint32, C.c_char_p]),
+    "apd_load_matrix": (C.c_int, [C.c_char_p, _fp, C.c_uint64, _u32p, C.c_int]),
+    "apd_save_paths": (C.c_int, [C.c_char_p, _u32p, C.c_uint64, _fp, _u32p, C.c_uint64, _u64p]),
+    "apd_load_paths": (C.c_int, [C.c_char_p, _u32p, _fp, _u64p, C.c_uint64, _u32p, C.c_uint64, _u64p]),
 }
 
 _lib = None

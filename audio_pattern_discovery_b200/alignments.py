@@ -49,18 +49,47 @@ def _c_params(pct, ins, dele, mat, mode):
     return apd_params(float(pct), float(ins), float(dele), float(mat), int(mode))
 
 
-class Context:
-    """One device context (apd_ctx): owns the packed sequence arena on one GPU."""
+def visible_devices():
+    """Number of CUDA devices the library sees (raises without one: there is no CPU path)."""
+    lib = _capi.lib()
+    n = C.c_int(0)
+    st = lib.apd_device_count(C.byref(n))
+    if st != _capi.APD_OK:
+        msg = lib.apd_last_error(None)
+        raise ApdError(st, msg.decode() if msg else "")
+    return n.value
 
-    def __init__(self, device=0):
+
+class Context:
+    """An apd_ctx: the packed sequence arena on one GPU (device=k), or -- from this one
+    process -- on a group of GPUs (devices=[...] or devices="all", apd_create_multi) that
+    shares the pair space and assembles the matrix over NVLink inside the library."""
+
+    def __init__(self, device=0, devices=None):
         self._lib = _capi.lib()
         h = C.c_void_p()
-        st = self._lib.apd_create(int(device), C.byref(h))
+        if devices is None:
+            st = self._lib.apd_create(int(device), C.byref(h))
+            self.devices = [int(device)]
+        elif isinstance(devices, str):
+            if devices != "all":
+                raise ValueError('devices must be a list of device ids or "all"')
+            st = self._lib.apd_create_multi(None, 0, C.byref(h))
+            self.devices = None
+        else:
+            ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+            st = self._lib.apd_create_multi(ids, len(devices), C.byref(h))
+            self.devices = [int(d) for d in devices]
         if st != _capi.APD_OK:
             msg = self._lib.apd_last_error(None)
             raise ApdError(st, msg.decode() if msg else "")
         self._h = h
-        self.device = int(device)
+        g, ps = C.c_uint32(0), C.c_uint32(0)
+        self._check(self._lib.apd_group_size(self._h, C.byref(g), C.byref(ps)))
+        self.group_size, self.peer_stores = g.value, bool(ps.value)
+        if self.devices is None:
+            self.devices = list(range(self.group_size))
+        self.device = self.devices[0]
         self.n = 0
         self.dim = 0
 
@@ -111,6 +140,36 @@ class Context:
         self._check(self._lib.apd_set_sequences(self._h, ptrs, lens.ctypes.data_as(_u32p), n, dim))
         self._keepalive = arrs  # the library copies before returning; kept only until the next call
         self.n, self.dim = n, dim
+
+    def set_sequences_encoded(self, cepstra, w_encode, b_encode):
+        """NDSequence::encoded on the device (src/spectrogram.rs:103-121, src/neural.rs:55-71):
+        cepstra = list of (T, n_bins) float32 arrays, w_encode (n_bins, n_latent), b_encode
+        (n_latent,).  The embeddings are written into the arena; frame width becomes n_latent."""
+        arrs = [s.as_array() if isinstance(s, NDSequence) else np.ascontiguousarray(s, dtype=np.float32) for s in cepstra]
+        w = np.ascontiguousarray(w_encode, dtype=np.float32)
+        b = np.ascontiguousarray(b_encode, dtype=np.float32).ravel()
+        if w.ndim != 2 or b.size != w.shape[1]:
+            raise ValueError("w_encode must be (n_bins, n_latent) and b_encode (n_latent,)")
+        n_bins, n_latent = w.shape
+        for a in arrs:
+            if a.ndim != 2 or (a.shape[0] and a.shape[1] != n_bins):
+                raise ValueError("every cepstrum must be (T, n_bins)")
+        n = len(arrs)
+        addr = np.fromiter((a.__array_interface__["data"][0] for a in arrs), dtype=np.uintp, count=n)
+        if n == 0:
+            addr = np.zeros(1, dtype=np.uintp)
+        lens = np.fromiter((a.shape[0] for a in arrs), dtype=np.uint32, count=n)
+        self._check(self._lib.apd_set_sequences_encoded(
+            self._h, addr.ctypes.data_as(C.POINTER(_fp)), lens.ctypes.data_as(_u32p), n, n_bins,
+            w.ctypes.data_as(_fp), b.ctypes.data_as(_fp), n_latent))
+        self._lens = lens
+        self.n, self.dim = n, n_latent
+
+    def get_sequence(self, index, length):
+        """One sequence of the device arena, (length, dim) float32 (what the kernels read)."""
+        out = np.empty((int(length), self.dim), dtype=np.float32)
+        self._check(self._lib.apd_get_sequence(self._h, int(index), out.ctypes.data_as(_fp), out.size))
+        return out
 
     def set_sequences_flat(self, flat, offsets, lens, dim):
         flat = np.ascontiguousarray(flat, dtype=np.float32)
@@ -192,6 +251,11 @@ class Context:
                                                     C.c_void_p(stream), C.byref(out)))
         return np.float32(out.value)
 
+    def launch_plan(self):
+        """Launch classes of the last DTW enqueue (ring home, ring height, units, grid)."""
+        import json
+        return json.loads(self._lib.apd_last_launch_plan(self._h).decode())
+
     def stats(self):
         s = apd_stats()
         self._check(self._lib.apd_get_stats(self._h, C.byref(s)))
@@ -224,17 +288,22 @@ class AlignmentWorkers:
     spread over the GPU by the library, not over host threads.
     """
 
-    def __init__(self, data, device=0, mode=APD_MODE_STRICT):
+    def __init__(self, data, device=None, mode=APD_MODE_STRICT, devices=None):
         self.data = list(data)
         n = len(self.data)
         self.result = _Mutex(np.zeros(n * n, dtype=np.float32))  # diag stays 0.0 (src/alignments.rs:20-23,51)
         self.mode = mode
-        self._ctx = Context(device)
+        # Like the reference's one blocking call from one process (src/main.rs:189-195), but
+        # spread over every visible GPU unless the caller names one (device=k) or some (devices=[..]).
+        if device is not None:
+            self._ctx = Context(device)
+        else:
+            self._ctx = Context(devices="all" if devices is None else devices)
         self._ctx.set_sequences(self.data)
 
     @staticmethod
-    def new(data, device=0, mode=APD_MODE_STRICT):
-        return AlignmentWorkers(data, device, mode)
+    def new(data, device=None, mode=APD_MODE_STRICT, devices=None):
+        return AlignmentWorkers(data, device, mode, devices)
 
     def align_all(self, params):
         """params: a Discovery (src/discovery.rs:7-26).  Blocking; fills self.result."""

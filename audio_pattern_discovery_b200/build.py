@@ -22,6 +22,10 @@ OBJ = os.path.join(ROOT, "build", "obj")
 LIB = os.path.join(HERE, "libapd_b200.so")
 
 DPADS = (4, 8, 12, 16, 20, 24, 28, 32)
+# Translation units besides dtw_inst.cu (once per padded width).  rust/apd-sys/build.rs lists
+# the same files; tests/test_rust_sources.py compares the two lists.
+CUDA_UNITS = ("apd_api", "pair_path", "percentile", "ae_encode")
+CXX_UNITS = ("host_plan", "upgma", "matrix_io")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-D%s=%s" % (k, os.environ[k]) for k in ("APD_X_LOOK", "APD_USE_EDGE_VARIANT", "APD_X_STAGE_TMA") if os.environ.get(k)] + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fno-fast-math,-ffp-contract=off"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unknown-pragmas"]
@@ -71,11 +75,11 @@ def build(force=False, verbose=False, ptxas_info=False):
         o = os.path.join(OBJ, "dtw_inst_%d.o" % d)
         objs.append(o)
         jobs.append([nvcc] + NVCC_FLAGS + extra + ["-DAPD_DPAD=%d" % d, "-c", "-o", o, os.path.join(CSRC, "dtw_inst.cu")])
-    for name in ("apd_api", "pair_path", "percentile"):
+    for name in CUDA_UNITS:
         o = os.path.join(OBJ, name + ".o")
         objs.append(o)
         jobs.append([nvcc] + NVCC_FLAGS + extra + ["-c", "-o", o, os.path.join(CSRC, name + ".cu")])
-    for name in ("host_plan", "upgma"):
+    for name in CXX_UNITS:
         o = os.path.join(OBJ, name + ".o")
         objs.append(o)
         jobs.append(["g++"] + CXX_FLAGS + ["-c", "-o", o, os.path.join(CSRC, name + ".cpp")])

@@ -2,11 +2,21 @@
 //
 // There is no CPU path in this file: every entry point that computes anything needs
 // a CUDA device, and apd_create() fails with APD_ERR_NO_DEVICE without one.
+//
+// A context drives one device (apd_create) or, from ONE host process, a group of up to
+// APD_MAX_GROUP devices of one box (apd_create_multi).  In a group the member with index 0 is
+// the leader: it owns the host-side state (arena layout, unit plan, statistics); every member
+// holds the whole sequence arena, computes the work units u with u % G == its index, and its
+// DTW kernel stores the packed results directly into the gathered buffer of every member
+// through NVLink peer mappings (KernelArgs::out) -- the all-gather is fused into the kernel.
+// Each member then expands the gathered buffer into the n x n matrix and copies its own slab
+// of rows to the caller's host buffer, so the device->host copy runs on G PCIe links at once.
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -14,6 +24,8 @@
 #include <vector>
 
 #include "../../include/apd.h"
+#include "ae_encode.cuh"
+#include "apd_internal.h"
 #include "dtw_kernels.cuh"
 #include "host_plan.h"
 #include "pair_path.cuh"
@@ -21,10 +33,12 @@
 
 using namespace apd;
 
-// The layouts the ctypes / Rust / C++ bindings mirror (tests/test_abi.py checks the Python side).
+// The layouts the ctypes / Rust / C++ bindings mirror (tests/test_abi.py checks the Python side,
+// tests/test_rust_sources.py the Rust side).
 static_assert(sizeof(apd_params) == 20, "apd_params layout is part of the ABI");
 static_assert(sizeof(apd_stats) == 104, "apd_stats layout is part of the ABI");
 static_assert(sizeof(apd_merge) == 24, "apd_merge layout is part of the ABI");
+static_assert(APD_MAX_DEVICES == APD_MAX_GROUP, "include/apd.h and dtw_kernels.cuh disagree on the group size");
 
 namespace {
 
@@ -32,52 +46,90 @@ thread_local std::string g_create_error;
 
 struct OccKey { int dpad, strict, unitw, ring; size_t smem; int occ; };
 
+struct DevStatus {            // device-side flags of one align call, read back in one copy
+    int error;                // a unit needed a bigger ring than planned
+    int pad;
+    unsigned long long tiles; // lane-tiles executed (statistics)
+};
+
+enum { STAGE_BUFS = 3, MAX_CLASSES = SMEM_RING_CAPS + 1 };
+const size_t kStageBytes = 16u << 20;  // one buffer of the pinned upload ring
+
 }  // namespace
 
+namespace apd {
+void set_thread_error(const std::string& msg) { g_create_error = msg; }
+}  // namespace apd
+
 struct apd_ctx {
+    // ---- device-local state ------------------------------------------------------------
     int device = 0;
     cudaStream_t stream = nullptr;
     int sm_count = 0;
     float sm_clock_mhz = 0.f;
     size_t smem_optin = 0;
 
-    Arena arena;  // layout only (data lives on the device)
-    bool have_sequences = false;
     float* d_arena = nullptr; size_t arena_cap = 0;
     uint32_t* d_off = nullptr; uint32_t* d_len = nullptr; uint32_t* d_perm = nullptr;
     uint64_t* d_srcoff = nullptr; size_t table_cap = 0;
-    float* h_stage = nullptr; size_t stage_cap = 0;  // pinned
     float* d_raw = nullptr; size_t raw_cap = 0;
+    float* d_aux = nullptr; size_t aux_cap = 0;          // auto-encoder weights (apd_set_sequences_encoded)
 
-    uint32_t rank = 0, world = 1;
-
-    UnitPlan plan; bool plan_valid = false;
     Unit* d_units = nullptr; size_t units_cap = 0;
-    uint64_t cells_ref = 0; bool cells_ref_valid = false;
+    uint64_t units_serial = 0;                           // serial of the plan d_units holds
 
-    float* d_packed = nullptr; size_t packed_cap = 0;   // own packed buffer (apd_align_all)
+    float* d_packed = nullptr; size_t packed_cap = 0;    // packed results: own shard, or (group) every member's, rank-major
     float* d_matrix = nullptr; size_t matrix_cap = 0;
     float2* d_gstate = nullptr; size_t gstate_cap = 0;
-    unsigned int* d_counters = nullptr;                 // one work counter per class
-    int* d_error = nullptr;
-    unsigned long long* d_tiles = nullptr;
-    unsigned long long* d_hist = nullptr;               // 256 radix-select counters
-    bool matrix_valid = false;                          // d_matrix holds the last apd_align_all result
+    unsigned int* d_counters = nullptr;                  // one work counter per launch class
+    DevStatus* d_status = nullptr;
+    DevStatus* h_status = nullptr;                       // pinned
+    unsigned long long* d_hist = nullptr;                // 256 radix-select counters
 
+    cudaStream_t class_stream[MAX_CLASSES] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_CLASSES] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr, ev_s0 = nullptr, ev_s1 = nullptr;
     cudaEvent_t ev_h0 = nullptr, ev_h1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
+    cudaEvent_t ev_done = nullptr;   // the last work enqueued by this library that touches the context's device state
+    cudaEvent_t ev_dtw = nullptr;    // group: this member's DTW kernels (and their peer stores) are complete
+    bool inflight = false;
     bool timed_kernel = false, timed_scatter = false, timed_h2d = false, timed_d2h = false;
-
     std::vector<OccKey> occ_cache;
+    float kernel_ms = 0.f, scatter_ms = 0.f;             // per-member timings of the last call
+    uint32_t launches = 0;
+    uint64_t local_units = 0;
+    unsigned long long tiles = 0;
+
+    // ---- group ---------------------------------------------------------------------------
+    apd_ctx* lead = nullptr;                 // == this for a single-device context and for the leader
+    std::vector<apd_ctx*> members;           // leader only: every member, members[0] == leader
+    bool p2p = false;                        // leader: every member can store into every member's memory
+    uint32_t rank = 0, world = 1;            // shard: multi-process (apd_set_shard) or index / size of the group
+
+    // ---- host-side state (leader / single) -------------------------------------------------
+    Arena arena;                             // layout only (data lives on the device)
+    bool have_sequences = false;
+    UnitPlan plan; bool plan_valid = false; uint64_t plan_serial = 0;
+    uint64_t cells_ref = 0; bool cells_ref_valid = false;
+    bool matrix_valid = false;               // d_matrix (of the leader) holds the last apd_align_all result
+    float* h_stage[STAGE_BUFS] = {nullptr, nullptr, nullptr};   // pinned upload ring
+    void* h_stage_raw[STAGE_BUFS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_stage[STAGE_BUFS] = {nullptr, nullptr, nullptr};
+    int ring_floor = RING_TMEM;              // APD_RING / APD_FORCE_GSTATE, read once at creation
+    bool debug = false;                      // APD_DEBUG
+    bool concurrent_classes = true;          // APD_SERIAL_CLASSES=1 turns it off
+
     apd_stats stats{};
     std::string err;
+    std::string launch_desc;                 // launch classes of the last DTW enqueue (apd_last_launch_plan)
 };
 
 namespace {
 
 apd_status fail(apd_ctx* c, apd_status s, const std::string& msg)
 {
-    if (c) c->err = msg; else g_create_error = msg;
+    if (c) { c->err = msg; if (c->lead && c->lead != c) c->lead->err = msg; }
+    else g_create_error = msg;
     return s;
 }
 
@@ -96,6 +148,24 @@ apd_status ensure_device(apd_ctx* c, T*& ptr, size_t& cap, size_t need_elems)
     size_t n = std::max<size_t>(need_elems, 1);
     APD_CUDA(c, cudaMalloc((void**)&ptr, n * sizeof(T)));
     cap = n;
+    return APD_OK;
+}
+
+inline bool grouped(const apd_ctx* c) { return c->lead->members.size() > 1; }
+
+// Work this library enqueued earlier (possibly on a caller's stream) may still be using the
+// context's shared device state (unit list, counters, status, ring scratch, packed buffer):
+// anything that is about to touch that state on `stream` is ordered behind it ...
+apd_status guard_begin(apd_ctx* c, cudaStream_t stream)
+{
+    if (c->inflight) APD_CUDA(c, cudaStreamWaitEvent(stream, c->ev_done, 0));
+    return APD_OK;
+}
+// ... and becomes the new "last work".
+apd_status guard_end(apd_ctx* c, cudaStream_t stream)
+{
+    APD_CUDA(c, cudaEventRecord(c->ev_done, stream));
+    c->inflight = true;
     return APD_OK;
 }
 
@@ -158,40 +228,43 @@ __global__ void pack_arena_kernel(const float* __restrict__ raw, const uint64_t*
     }
 }
 
-apd_status upload_tables(apd_ctx* c, const uint64_t* src_off_sorted)
+// Sorted-order tables of the leader's arena layout -> device m.
+apd_status upload_tables(apd_ctx* m, const uint64_t* src_off_sorted)
 {
-    const Arena& ar = c->arena;
+    const Arena& ar = m->lead->arena;
     const size_t n = ar.n;
-    if (n > c->table_cap || !c->d_off) {
-        if (c->d_off) cudaFree(c->d_off);
-        if (c->d_len) cudaFree(c->d_len);
-        if (c->d_perm) cudaFree(c->d_perm);
-        if (c->d_srcoff) cudaFree(c->d_srcoff);
-        c->d_off = c->d_len = c->d_perm = nullptr; c->d_srcoff = nullptr; c->table_cap = 0;
+    if (n > m->table_cap || !m->d_off) {
+        if (m->d_off) cudaFree(m->d_off);
+        if (m->d_len) cudaFree(m->d_len);
+        if (m->d_perm) cudaFree(m->d_perm);
+        if (m->d_srcoff) cudaFree(m->d_srcoff);
+        m->d_off = m->d_len = m->d_perm = nullptr; m->d_srcoff = nullptr; m->table_cap = 0;
         size_t cap = std::max<size_t>(n, 1);
-        APD_CUDA(c, cudaMalloc((void**)&c->d_off, cap * sizeof(uint32_t)));
-        APD_CUDA(c, cudaMalloc((void**)&c->d_len, cap * sizeof(uint32_t)));
-        APD_CUDA(c, cudaMalloc((void**)&c->d_perm, cap * sizeof(uint32_t)));
-        APD_CUDA(c, cudaMalloc((void**)&c->d_srcoff, cap * sizeof(uint64_t)));
-        c->table_cap = cap;
+        APD_CUDA(m, cudaMalloc((void**)&m->d_off, cap * sizeof(uint32_t)));
+        APD_CUDA(m, cudaMalloc((void**)&m->d_len, cap * sizeof(uint32_t)));
+        APD_CUDA(m, cudaMalloc((void**)&m->d_perm, cap * sizeof(uint32_t)));
+        APD_CUDA(m, cudaMalloc((void**)&m->d_srcoff, cap * sizeof(uint64_t)));
+        m->table_cap = cap;
     }
     if (n) {
-        APD_CUDA(c, cudaMemcpyAsync(c->d_off, ar.off.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        APD_CUDA(c, cudaMemcpyAsync(c->d_len, ar.len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        APD_CUDA(c, cudaMemcpyAsync(c->d_perm, ar.perm.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        APD_CUDA(m, cudaMemcpyAsync(m->d_off, ar.off.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
+        APD_CUDA(m, cudaMemcpyAsync(m->d_len, ar.len.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
+        APD_CUDA(m, cudaMemcpyAsync(m->d_perm, ar.perm.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, m->stream));
         if (src_off_sorted)
-            APD_CUDA(c, cudaMemcpyAsync(c->d_srcoff, src_off_sorted, n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+            APD_CUDA(m, cudaMemcpyAsync(m->d_srcoff, src_off_sorted, n * sizeof(uint64_t), cudaMemcpyHostToDevice, m->stream));
     }
     return APD_OK;
 }
 
+// Start of every apd_set_sequences*: validates, builds the layout on the leader, sizes the
+// arena on every member, and orders the coming uploads behind any kernels still in flight.
 apd_status begin_sequences(apd_ctx* c, const uint32_t* lens, uint32_t n, uint32_t dim)
 {
     if (!c) return APD_ERR_INVALID;
+    if (c->lead != c) return fail(c, APD_ERR_INVALID, "not a context handle returned by apd_create / apd_create_multi");
     if (dim == 0) return fail(c, APD_ERR_INVALID, "dim must be >= 1");
     if (dim > APD_MAX_DIM) return fail(c, APD_ERR_UNSUPPORTED, "dim > APD_MAX_DIM (32) is not supported");
     if (n > 0 && !lens) return fail(c, APD_ERR_INVALID, "lens is NULL");
-    APD_CUDA(c, cudaSetDevice(c->device));
     const bool had = c->have_sequences;
     c->have_sequences = false;
     c->matrix_valid = false;
@@ -208,7 +281,34 @@ apd_status begin_sequences(apd_ctx* c, const uint32_t* lens, uint32_t n, uint32_
         c->cells_ref_valid = false;
     }
     c->arena = std::move(next);
-    return ensure_device(c, c->d_arena, c->arena_cap, (size_t)c->arena.total_frames * c->arena.dpad);
+    for (apd_ctx* m : c->members) {
+        APD_CUDA(m, cudaSetDevice(m->device));
+        apd_status s = guard_begin(m, m->stream);
+        if (s != APD_OK) return s;
+        s = ensure_device(m, m->d_arena, m->arena_cap, (size_t)c->arena.total_frames * c->arena.dpad);
+        if (s != APD_OK) return s;
+    }
+    APD_CUDA(c, cudaSetDevice(c->device));
+    return APD_OK;
+}
+
+// End of every apd_set_sequences*: the leader's arena is complete on its stream (event ev_h1
+// recorded by the caller); the other members of a group pull it over NVLink.
+apd_status broadcast_arena(apd_ctx* c)
+{
+    const size_t bytes = (size_t)c->arena.total_frames * c->arena.dpad * sizeof(float);
+    for (apd_ctx* m : c->members) {
+        if (m == c) continue;
+        APD_CUDA(m, cudaSetDevice(m->device));
+        apd_status s = upload_tables(m, nullptr);
+        if (s != APD_OK) return s;
+        APD_CUDA(m, cudaStreamWaitEvent(m->stream, c->ev_h1, 0));
+        APD_CUDA(m, cudaMemcpyPeerAsync(m->d_arena, m->device, c->d_arena, c->device, bytes, m->stream));
+        s = guard_end(m, m->stream);
+        if (s != APD_OK) return s;
+    }
+    APD_CUDA(c, cudaSetDevice(c->device));
+    return guard_end(c, c->stream);
 }
 
 void k_range(uint64_t begin, uint64_t end, uint32_t rank, uint32_t world, uint64_t& k0, uint64_t& k1)
@@ -219,26 +319,53 @@ void k_range(uint64_t begin, uint64_t end, uint32_t rank, uint32_t world, uint64
     k1 = first_k(end);
 }
 
+// Packed (score(a,b), score(b,a)) entries per shard -- identical on every rank / member.
 uint64_t packed_entries(const apd_ctx* c)
 {
-    uint64_t U = c->plan.units.size();
-    return (U + c->world - 1) / c->world;  // identical on every rank
+    const apd_ctx* L = c->lead;
+    uint64_t U = L->plan.units.size();
+    return (U + c->world - 1) / c->world;
 }
 
+// Host plan on the leader (a pure function of the sorted lengths and pct), then the unit list
+// on every member: the leader's copy comes from the host, the other members pull it from the
+// leader over NVLink.
 apd_status ensure_plan(apd_ctx* c, float pct)
 {
     // The plan depends on pct only through the band (bit pattern compare keeps NaN stable).
-    if (c->plan_valid && std::memcmp(&c->plan.pct, &pct, sizeof(float)) == 0) return APD_OK;
-    build_unit_plan(c->arena, pct, c->plan);
-    c->cells_ref_valid = false;
-    apd_status s = ensure_device(c, c->d_units, c->units_cap, c->plan.units.size());
-    if (s != APD_OK) return s;
-    if (!c->plan.units.empty())
-        APD_CUDA(c, cudaMemcpyAsync(c->d_units, c->plan.units.data(), c->plan.units.size() * sizeof(Unit),
-                                    cudaMemcpyHostToDevice, c->stream));
-    // the host vector must outlive the async copy from pageable memory: it does (owned by ctx),
-    // and cudaMemcpyAsync from pageable memory returns only after staging the source.
-    c->plan_valid = true;
+    if (!(c->plan_valid && std::memcmp(&c->plan.pct, &pct, sizeof(float)) == 0)) {
+        build_unit_plan(c->arena, pct, c->plan);
+        c->cells_ref_valid = false;
+        c->plan_valid = true;
+        c->plan_serial++;
+    }
+    const size_t nu = c->plan.units.size();
+    if (c->units_serial != c->plan_serial) {
+        APD_CUDA(c, cudaSetDevice(c->device));
+        apd_status s = guard_begin(c, c->stream);   // kernels of an earlier call may still read d_units
+        if (s != APD_OK) return s;
+        s = ensure_device(c, c->d_units, c->units_cap, nu);
+        if (s != APD_OK) return s;
+        // (cudaMemcpyAsync from pageable memory returns after staging the source; the vector is owned by the context)
+        if (nu) APD_CUDA(c, cudaMemcpyAsync(c->d_units, c->plan.units.data(), nu * sizeof(Unit), cudaMemcpyHostToDevice, c->stream));
+        s = guard_end(c, c->stream);
+        if (s != APD_OK) return s;
+        c->units_serial = c->plan_serial;
+    }
+    for (apd_ctx* m : c->members) {
+        if (m == c || m->units_serial == c->plan_serial) continue;
+        APD_CUDA(m, cudaSetDevice(m->device));
+        apd_status s = guard_begin(m, m->stream);
+        if (s != APD_OK) return s;
+        s = ensure_device(m, m->d_units, m->units_cap, nu);
+        if (s != APD_OK) return s;
+        APD_CUDA(m, cudaStreamWaitEvent(m->stream, c->ev_done, 0));
+        if (nu) APD_CUDA(m, cudaMemcpyPeerAsync(m->d_units, m->device, c->d_units, c->device, nu * sizeof(Unit), m->stream));
+        s = guard_end(m, m->stream);
+        if (s != APD_OK) return s;
+        m->units_serial = c->plan_serial;
+    }
+    APD_CUDA(c, cudaSetDevice(c->device));
     return APD_OK;
 }
 
@@ -265,145 +392,201 @@ apd_status check_params(apd_ctx* c, const apd_params* p)
     return APD_OK;
 }
 
-apd_status run_dtw(apd_ctx* c, const apd_params* p, float* d_packed, cudaStream_t stream)
+// Enqueues the DTW kernels of member / context m's shard on `stream`: one launch per class of
+// the plan, most expensive class first, each class on its own stream so that the tail of one
+// launch is filled by the next (the classes share nothing but the output buffers).
+// outs[0..n_out): where the packed results go (see KernelArgs::out).
+apd_status run_dtw(apd_ctx* m, const apd_params* p, float* const* outs, uint32_t n_out, cudaStream_t stream)
 {
+    apd_ctx* L = m->lead;
+    const Arena& ar = L->arena;
+    const UnitPlan& plan = L->plan;
     LaunchFns f;
-    if (!pick_launcher(c->arena.dpad, f)) return fail(c, APD_ERR_UNSUPPORTED, "unsupported frame width");
+    if (!pick_launcher(ar.dpad, f)) return fail(m, APD_ERR_UNSUPPORTED, "unsupported frame width");
     const bool strict = (p->mode == APD_MODE_STRICT);
     const bool unitw = (p->insertion_penalty == 1.0f && p->deletion_penalty == 1.0f && p->match_penalty == 1.0f);
     // Where the boundary ring lives (dtw_kernels.cuh): tensor memory if it fits 256 columns,
-    // else shared memory, else global scratch.  APD_RING=tmem|smem|global narrows the choice
-    // for experiments and tests (a ring that does not fit the forced home moves down the list).
-    const char* ring_env = getenv("APD_RING");
-    const char* force_g = getenv("APD_FORCE_GSTATE");
-    int ring_floor = RING_TMEM;  // best allowed: TMEM > SMEM > GLOBAL
-    if (ring_env && !strcmp(ring_env, "smem")) ring_floor = RING_SMEM;
-    if ((ring_env && !strcmp(ring_env, "global")) || (force_g && force_g[0] == '1')) ring_floor = RING_GLOBAL;
+    // else shared memory, else global scratch.  APD_RING=tmem|smem|global (read at creation)
+    // narrows the choice for experiments and tests (a ring that does not fit the forced home
+    // moves down the list).
+    const int ring_floor = L->ring_floor;
 
-    APD_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 8 * sizeof(unsigned int), stream));
-    APD_CUDA(c, cudaMemsetAsync(c->d_error, 0, sizeof(int), stream));
-    APD_CUDA(c, cudaMemsetAsync(c->d_tiles, 0, sizeof(unsigned long long), stream));
-    APD_CUDA(c, cudaEventRecord(c->ev_k0, stream));
+    apd_status s = guard_begin(m, stream);
+    if (s != APD_OK) return s;
+    APD_CUDA(m, cudaMemsetAsync(m->d_counters, 0, 8 * sizeof(unsigned int), stream));
+    APD_CUDA(m, cudaMemsetAsync(m->d_status, 0, sizeof(DevStatus), stream));
+    APD_CUDA(m, cudaEventRecord(m->ev_k0, stream));
     uint32_t launches = 0;
     uint64_t local_units = 0;
-    for (size_t ci = 0; ci < c->plan.classes.size(); ci++) {
-        const UnitClass& uc = c->plan.classes[ci];
-        uint64_t k0, k1;
-        k_range(uc.begin, uc.end, c->rank, c->world, k0, k1);
-        if (k1 <= k0) continue;
-        local_units += k1 - k0;
-        int ring = RING_GLOBAL;
-        if (ring_floor == RING_TMEM && uc.St <= TMEM_RING_TILES) ring = RING_TMEM;
-        else if (ring_floor != RING_GLOBAL && !uc.gstate) ring = RING_SMEM;
-        const size_t smem = dtw_smem_bytes((int)c->arena.dpad, uc.St, ring);
-        if (smem > c->smem_optin) return fail(c, APD_ERR_INTERNAL, "ring does not fit in shared memory");
-        int occ = 0;
-        apd_status s = occupancy(c, f, (int)c->arena.dpad, strict, unitw, ring, smem, occ);
+    const size_t ncls = plan.classes.size();
+    if (ncls > MAX_CLASSES) return fail(m, APD_ERR_INTERNAL, "too many launch classes");
+
+    // ring scratch of the global-ring class is sized before anything is launched (no realloc mid-flight)
+    struct Cls { uint64_t k0, k1; int ring, occ, grid; size_t smem; };
+    Cls cls[MAX_CLASSES];
+    size_t gstate_need = 0;
+    for (size_t ci = 0; ci < ncls; ci++) {
+        const UnitClass& uc = plan.classes[ci];
+        Cls& q = cls[ci];
+        k_range(uc.begin, uc.end, m->rank, m->world, q.k0, q.k1);
+        if (q.k1 <= q.k0) continue;
+        q.ring = RING_GLOBAL;
+        if (ring_floor == RING_TMEM && uc.St <= TMEM_RING_TILES) q.ring = RING_TMEM;
+        else if (ring_floor != RING_GLOBAL && !uc.gstate) q.ring = RING_SMEM;
+        q.smem = dtw_smem_bytes((int)ar.dpad, uc.St, q.ring);
+        if (q.smem > m->smem_optin) return fail(m, APD_ERR_INTERNAL, "ring does not fit in shared memory");
+        s = occupancy(m, f, (int)ar.dpad, strict, unitw, q.ring, q.smem, q.occ);
         if (s != APD_OK) return s;
-        const uint64_t warps_per_cta = (uint64_t)dtw_cta_warps(ring);
-        uint64_t grid64 = std::min<uint64_t>((k1 - k0 + warps_per_cta - 1) / warps_per_cta, (uint64_t)c->sm_count * occ);
-        int grid = (int)grid64;
+        const uint64_t wpc = (uint64_t)dtw_cta_warps(q.ring);
+        q.grid = (int)std::min<uint64_t>((q.k1 - q.k0 + wpc - 1) / wpc, (uint64_t)m->sm_count * q.occ);
+        if (q.ring == RING_GLOBAL) gstate_need += (size_t)q.grid * uc.St * TILE * 32;
+    }
+    s = ensure_device(m, m->d_gstate, m->gstate_cap, gstate_need);
+    if (s != APD_OK) return s;
+
+    m->launch_desc.clear();
+    const bool fork = L->concurrent_classes && ncls > 1;
+    if (fork) APD_CUDA(m, cudaEventRecord(m->ev_fork, stream));
+    size_t gstate_used = 0;
+    for (size_t cr = 0; cr < ncls; cr++) {
+        const size_t ci = ncls - 1 - cr;   // classes are ordered by ring height: the tallest (most expensive units) first
+        const UnitClass& uc = plan.classes[ci];
+        const Cls& q = cls[ci];
+        if (q.k1 <= q.k0) continue;
+        local_units += q.k1 - q.k0;
         KernelArgs a{};
-        a.arena = c->d_arena; a.off = c->d_off; a.len = c->d_len; a.units = c->d_units;
-        a.N = c->arena.n; a.rank = c->rank; a.world = c->world;
-        a.k_begin = k0; a.k_count = (uint32_t)(k1 - k0);
-        a.counter = c->d_counters + ci;
+        a.arena = m->d_arena; a.off = m->d_off; a.len = m->d_len; a.units = m->d_units;
+        a.N = ar.n; a.rank = m->rank; a.world = m->world;
+        a.k_begin = q.k0; a.k_count = (uint32_t)(q.k1 - q.k0);
+        a.counter = m->d_counters + ci;
         a.pct = p->warping_band_percentage;
         a.pen.ins = p->insertion_penalty; a.pen.del = p->deletion_penalty; a.pen.mat = p->match_penalty;
         a.St = uc.St;
-        a.out = reinterpret_cast<float2*>(d_packed);
-        a.error_flag = c->d_error;
-        a.tiles_done = c->d_tiles;
-        if (ring == RING_GLOBAL) {
-            size_t need = (size_t)grid * uc.St * TILE * 32;
-            s = ensure_device(c, c->d_gstate, c->gstate_cap, need);
-            if (s != APD_OK) return s;
-            a.gstate = c->d_gstate;
+        for (uint32_t o = 0; o < n_out; o++) a.out[o] = reinterpret_cast<float2*>(outs[o]);
+        a.n_out = n_out;
+        a.error_flag = &m->d_status->error;
+        a.tiles_done = &m->d_status->tiles;
+        if (q.ring == RING_GLOBAL) {
+            a.gstate = m->d_gstate + gstate_used;
+            gstate_used += (size_t)q.grid * uc.St * TILE * 32;
         }
-        if (getenv("APD_DEBUG"))
-            fprintf(stderr, "[apd] class %zu: ring=%s St=%d units=%llu grid=%d x %d warps occ=%d smem=%zu\n", ci,
-                    ring == RING_TMEM ? "tmem" : (ring == RING_SMEM ? "smem" : "global"), uc.St,
-                    (unsigned long long)(k1 - k0), grid, (int)warps_per_cta, occ, smem);
-        APD_CUDA(c, f.launch(a, strict, unitw, ring, grid, smem, stream));
+        {
+            char line[256];
+            snprintf(line, sizeof(line), "%s{\"ring\": \"%s\", \"ring_tiles\": %d, \"units\": %llu, \"ctas\": %d, \"warps_per_cta\": %d, "
+                     "\"ctas_per_sm\": %d, \"smem_bytes\": %zu}", m->launch_desc.empty() ? "" : ", ",
+                     q.ring == RING_TMEM ? "tmem" : (q.ring == RING_SMEM ? "smem" : "global"), uc.St,
+                     (unsigned long long)(q.k1 - q.k0), q.grid, dtw_cta_warps(q.ring), q.occ, q.smem);
+            m->launch_desc += line;
+            if (L->debug) fprintf(stderr, "[apd] dev %d class %zu: %s\n", m->device, ci, line);
+        }
+        cudaStream_t ls = stream;
+        if (fork && launches > 0) {
+            ls = m->class_stream[ci];
+            APD_CUDA(m, cudaStreamWaitEvent(ls, m->ev_fork, 0));
+        }
+        APD_CUDA(m, f.launch(a, strict, unitw, q.ring, q.grid, q.smem, ls));
+        if (ls != stream) {
+            APD_CUDA(m, cudaEventRecord(m->ev_join[ci], ls));
+            APD_CUDA(m, cudaStreamWaitEvent(stream, m->ev_join[ci], 0));
+        }
         launches++;
     }
-    APD_CUDA(c, cudaEventRecord(c->ev_k1, stream));
-    c->timed_kernel = true;
-    c->stats.kernel_launches = launches;
-    c->stats.units_local = local_units;
-    c->stats.units_total = c->plan.units.size();
-    return APD_OK;
+    APD_CUDA(m, cudaEventRecord(m->ev_k1, stream));
+    m->timed_kernel = true;
+    m->launches = launches;
+    m->local_units = local_units;
+    return guard_end(m, stream);
 }
 
-apd_status run_scatter(apd_ctx* c, const float* d_gathered, uint32_t nranks, float* d_out, cudaStream_t stream)
+apd_status run_scatter(apd_ctx* m, const float* d_gathered, uint32_t nranks, float* d_out, cudaStream_t stream)
 {
-    const uint64_t N = c->arena.n;
-    APD_CUDA(c, cudaEventRecord(c->ev_s0, stream));
-    if (N) APD_CUDA(c, cudaMemsetAsync(d_out, 0, N * N * sizeof(float), stream));
-    const uint64_t kpr = packed_entries(c);
+    apd_ctx* L = m->lead;
+    const uint64_t N = L->arena.n;
+    APD_CUDA(m, cudaEventRecord(m->ev_s0, stream));
+    if (N) APD_CUDA(m, cudaMemsetAsync(d_out, 0, N * N * sizeof(float), stream));
+    const uint64_t kpr = packed_entries(m);
     const uint64_t threads = (uint64_t)nranks * kpr * 32;
     if (threads) {
         const int bs = 256;
         const uint64_t blocks = (threads + bs - 1) / bs;
-        if (blocks > 0x7fffffffull) return fail(c, APD_ERR_UNSUPPORTED, "matrix too large for one scatter launch");
+        if (blocks > 0x7fffffffull) return fail(m, APD_ERR_UNSUPPORTED, "matrix too large for one scatter launch");
         // nranks == world: buffer holds all ranks (rank-major).  nranks == 1 on a sharded
         // context: buffer holds only this rank's units.
-        const uint32_t world = c->world;
-        if (nranks == world) {
-            scatter_packed_kernel<<<(unsigned)blocks, bs, 0, stream>>>(
-                reinterpret_cast<const float2*>(d_gathered), kpr, world, 0, c->d_units,
-                c->plan.units.size(), c->d_perm, (uint32_t)N, d_out);
-        } else {
-            scatter_packed_kernel<<<(unsigned)blocks, bs, 0, stream>>>(
-                reinterpret_cast<const float2*>(d_gathered), kpr, world, c->rank, c->d_units,
-                c->plan.units.size(), c->d_perm, (uint32_t)N, d_out);
-        }
-        APD_CUDA(c, cudaGetLastError());
-        c->stats.kernel_launches++;
+        const uint32_t world = m->world;
+        scatter_packed_kernel<<<(unsigned)blocks, bs, 0, stream>>>(
+            reinterpret_cast<const float2*>(d_gathered), kpr, world, nranks == world ? 0u : m->rank, m->d_units,
+            L->plan.units.size(), m->d_perm, (uint32_t)N, d_out);
+        APD_CUDA(m, cudaGetLastError());
+        m->launches++;
     }
-    APD_CUDA(c, cudaEventRecord(c->ev_s1, stream));
-    c->timed_scatter = true;
+    APD_CUDA(m, cudaEventRecord(m->ev_s1, stream));
+    m->timed_scatter = true;
+    return guard_end(m, stream);
+}
+
+// Waits for `stream` of member m and collects its status / timings.
+apd_status finish_member(apd_ctx* m, cudaStream_t stream)
+{
+    APD_CUDA(m, cudaMemcpyAsync(m->h_status, m->d_status, sizeof(DevStatus), cudaMemcpyDeviceToHost, stream));
+    APD_CUDA(m, cudaStreamSynchronize(stream));
+    m->inflight = false;
+    m->tiles = m->h_status->tiles;
+    if (m->timed_kernel) { cudaEventElapsedTime(&m->kernel_ms, m->ev_k0, m->ev_k1); m->timed_kernel = false; }
+    if (m->timed_scatter) { cudaEventElapsedTime(&m->scatter_ms, m->ev_s0, m->ev_s1); m->timed_scatter = false; }
+    if (m->h_status->error) return fail(m, APD_ERR_INTERNAL, "a work unit needed a larger boundary ring than planned");
     return APD_OK;
 }
 
-apd_status finish(apd_ctx* c, cudaStream_t stream)
+// Statistics of the last align call, aggregated over the members (max of the times, sums of the counts).
+void collect_stats(apd_ctx* c)
 {
-    APD_CUDA(c, cudaStreamSynchronize(stream));
-    int herr = 0;
-    unsigned long long tiles = 0;
-    APD_CUDA(c, cudaMemcpy(&herr, c->d_error, sizeof(int), cudaMemcpyDeviceToHost));
-    APD_CUDA(c, cudaMemcpy(&tiles, c->d_tiles, sizeof(tiles), cudaMemcpyDeviceToHost));
-    c->stats.cells_computed = (uint64_t)tiles * TILE * TILE * 2;
-    if (c->timed_kernel) { cudaEventElapsedTime(&c->stats.kernel_ms, c->ev_k0, c->ev_k1); c->timed_kernel = false; }
-    if (c->timed_scatter) { cudaEventElapsedTime(&c->stats.scatter_ms, c->ev_s0, c->ev_s1); c->timed_scatter = false; }
+    float kms = 0.f, sms = 0.f;
+    uint64_t tiles = 0, units = 0;
+    uint32_t launches = 0;
+    for (apd_ctx* m : c->members) {
+        kms = std::max(kms, m->kernel_ms); sms = std::max(sms, m->scatter_ms);
+        tiles += m->tiles; units += m->local_units; launches += m->launches;
+    }
+    c->stats.kernel_ms = kms; c->stats.scatter_ms = sms;
+    c->stats.cells_computed = tiles * TILE * TILE * 2;
+    c->stats.units_local = units;
+    c->stats.units_total = c->plan.units.size();
+    c->stats.kernel_launches = launches;
     if (c->timed_h2d) { cudaEventElapsedTime(&c->stats.h2d_ms, c->ev_h0, c->ev_h1); c->timed_h2d = false; }
     if (c->timed_d2h) { cudaEventElapsedTime(&c->stats.d2h_ms, c->ev_d0, c->ev_d1); c->timed_d2h = false; }
-    if (herr) return fail(c, APD_ERR_INTERNAL, "a work unit needed a larger boundary ring than planned");
+}
+
+void set_sequence_stats(apd_ctx* c, uint32_t n, uint64_t h2d_bytes)
+{
+    c->stats.h2d_bytes = h2d_bytes;
+    c->stats.n_sequences = n;
+    c->stats.ordered_pairs = (uint64_t)n * (n ? n - 1 : 0);
+}
+
+apd_status ensure_stage_ring(apd_ctx* c)
+{
+    if (c->h_stage[0]) return APD_OK;
+    for (int b = 0; b < STAGE_BUFS; b++) {
+        // page-aligned host memory, registered (pinned) in place: several times cheaper than
+        // cudaMallocHost, which matters for the first call of a fresh context
+        void* raw = nullptr;
+        if (posix_memalign(&raw, 4096, kStageBytes) != 0) return fail(c, APD_ERR_INTERNAL, "out of host memory");
+        std::memset(raw, 0, kStageBytes);
+        cudaError_t e = cudaHostRegister(raw, kStageBytes, cudaHostRegisterPortable);
+        if (e != cudaSuccess) { free(raw); return fail(c, APD_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+        c->h_stage_raw[b] = raw;
+        c->h_stage[b] = static_cast<float*>(raw);
+        APD_CUDA(c, cudaEventCreateWithFlags(&c->ev_stage[b], cudaEventDisableTiming));
+    }
     return APD_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-uint32_t apd_abi_version(void) { return APD_ABI_VERSION; }
-
-const char* apd_last_error(const apd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
-
-apd_status apd_create(int device_id, apd_ctx** out)
+apd_status create_one(int device_id, apd_ctx** out)
 {
-    if (!out) return fail(nullptr, APD_ERR_INVALID, "out is NULL");
-    *out = nullptr;
-    int count = 0;
-    cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0)
-        return fail(nullptr, APD_ERR_NO_DEVICE,
-                    std::string("no CUDA device (this library has no CPU path): ") +
-                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
-    if (device_id < 0 || device_id >= count) return fail(nullptr, APD_ERR_INVALID, "device_id out of range");
     apd_ctx* c = new (std::nothrow) apd_ctx();
     if (!c) return fail(nullptr, APD_ERR_INTERNAL, "out of host memory");
     c->device = device_id;
+    c->lead = c;
     cudaDeviceProp prop;
 #define APD_CREATE_CUDA(call)                                                            \
     do {                                                                                 \
@@ -428,32 +611,211 @@ apd_status apd_create(int device_id, apd_ctx** out)
     c->sm_clock_mhz = khz / 1000.0f;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     APD_CREATE_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int k = 0; k < MAX_CLASSES; k++) {
+        APD_CREATE_CUDA(cudaStreamCreateWithFlags(&c->class_stream[k], cudaStreamNonBlocking));
+        APD_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming));
+    }
     APD_CREATE_CUDA(cudaMalloc((void**)&c->d_counters, 8 * sizeof(unsigned int)));
-    APD_CREATE_CUDA(cudaMalloc((void**)&c->d_error, sizeof(int)));
-    APD_CREATE_CUDA(cudaMalloc((void**)&c->d_tiles, sizeof(unsigned long long)));
+    APD_CREATE_CUDA(cudaMalloc((void**)&c->d_status, sizeof(DevStatus)));
+    APD_CREATE_CUDA(cudaMemset(c->d_status, 0, sizeof(DevStatus)));
+    APD_CREATE_CUDA(cudaMallocHost((void**)&c->h_status, sizeof(DevStatus)));
     APD_CREATE_CUDA(cudaMalloc((void**)&c->d_hist, 256 * sizeof(unsigned long long)));
     cudaEvent_t* evs[] = {&c->ev_k0, &c->ev_k1, &c->ev_s0, &c->ev_s1, &c->ev_h0, &c->ev_h1, &c->ev_d0, &c->ev_d1};
     for (cudaEvent_t* ev : evs) APD_CREATE_CUDA(cudaEventCreate(ev));
+    APD_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+    APD_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_dtw, cudaEventDisableTiming));
+    APD_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 #undef APD_CREATE_CUDA
+    const char* ring_env = getenv("APD_RING");
+    const char* force_g = getenv("APD_FORCE_GSTATE");
+    if (ring_env && !strcmp(ring_env, "smem")) c->ring_floor = RING_SMEM;
+    if ((ring_env && !strcmp(ring_env, "global")) || (force_g && force_g[0] == '1')) c->ring_floor = RING_GLOBAL;
+    c->debug = getenv("APD_DEBUG") != nullptr;
+    const char* ser = getenv("APD_SERIAL_CLASSES");
+    c->concurrent_classes = !(ser && ser[0] == '1');
     c->stats.sm_clock_mhz = c->sm_clock_mhz;
     c->stats.sm_count = (uint32_t)c->sm_count;
+    c->members.push_back(c);
     *out = c;
+    return APD_OK;
+}
+
+void destroy_one(apd_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < MAX_CLASSES; k++) {
+        if (c->class_stream[k]) { cudaStreamSynchronize(c->class_stream[k]); cudaStreamDestroy(c->class_stream[k]); }
+        if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]);
+    }
+    void* dptrs[] = {c->d_arena, c->d_off, c->d_len, c->d_perm, c->d_srcoff, c->d_raw, c->d_aux, c->d_units, c->d_packed,
+                     c->d_matrix, c->d_gstate, c->d_counters, c->d_status, c->d_hist};
+    for (void* p : dptrs) if (p) cudaFree(p);
+    if (c->h_status) cudaFreeHost(c->h_status);
+    for (int b = 0; b < STAGE_BUFS; b++) {
+        if (c->h_stage_raw[b]) { cudaHostUnregister(c->h_stage_raw[b]); free(c->h_stage_raw[b]); }
+        if (c->ev_stage[b]) cudaEventDestroy(c->ev_stage[b]);
+    }
+    cudaEvent_t evs[] = {c->ev_k0, c->ev_k1, c->ev_s0, c->ev_s1, c->ev_h0, c->ev_h1, c->ev_d0, c->ev_d1,
+                         c->ev_done, c->ev_dtw, c->ev_fork};
+    for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// Chunked upload of the arena: host threads pack the next piece of the sorted, padded arena
+// into a pinned ring buffer while the previous pieces are on their way to HBM.  Returns when
+// the caller's buffers are no longer needed (the last pieces may still be in flight).
+apd_status upload_arena(apd_ctx* c, const float* const* frames)
+{
+    apd_status s = ensure_stage_ring(c);
+    if (s != APD_OK) return s;
+    const Arena& ar = c->arena;
+    const uint64_t frames_per_buf = std::max<uint64_t>(kStageBytes / (ar.dpad * sizeof(float)), 1);
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = std::max(1u, std::min(nt, 8u));
+    int b = 0;
+    uint64_t chunk = 0;
+    for (uint64_t F0 = 0; F0 < ar.total_frames; F0 += frames_per_buf, chunk++, b = (b + 1) % STAGE_BUFS) {
+        const uint64_t F1 = std::min<uint64_t>(F0 + frames_per_buf, ar.total_frames);
+        APD_CUDA(c, cudaEventSynchronize(c->ev_stage[b]));  // the last copy out of this buffer (if any) is done
+        float* dst = c->h_stage[b];
+        const uint64_t nf = F1 - F0;
+        const unsigned use = (nf * ar.dpad * sizeof(float) < (1u << 20)) ? 1u : nt;
+        if (use == 1) {
+            fill_arena_frames(ar, frames, F0, F1, dst);
+        } else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < use; t++) {
+                const uint64_t a = F0 + nf * t / use, e = F0 + nf * (t + 1) / use;
+                th.emplace_back([&ar, frames, a, e, dst, F0] { fill_arena_frames(ar, frames, a, e, dst + (a - F0) * ar.dpad); });
+            }
+            for (auto& x : th) x.join();
+        }
+        APD_CUDA(c, cudaMemcpyAsync(c->d_arena + F0 * ar.dpad, dst, nf * ar.dpad * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        APD_CUDA(c, cudaEventRecord(c->ev_stage[b], c->stream));
+    }
+    return APD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t apd_abi_version(void) { return APD_ABI_VERSION; }
+
+const char* apd_last_error(const apd_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+apd_status apd_device_count(int* count)
+{
+    if (!count) return APD_ERR_INVALID;
+    *count = 0;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, APD_ERR_NO_DEVICE,
+                    std::string("no CUDA device (this library has no CPU path): ") +
+                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    *count = n;
+    return APD_OK;
+}
+
+apd_status apd_create(int device_id, apd_ctx** out)
+{
+    if (!out) return fail(nullptr, APD_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    apd_status s = apd_device_count(&count);
+    if (s != APD_OK) return s;
+    if (device_id < 0 || device_id >= count) return fail(nullptr, APD_ERR_INVALID, "device_id out of range");
+    return create_one(device_id, out);
+}
+
+apd_status apd_create_multi(const int* device_ids, int n_dev, apd_ctx** out)
+{
+    if (!out) return fail(nullptr, APD_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    apd_status s = apd_device_count(&count);
+    if (s != APD_OK) return s;
+    if (n_dev <= 0) { n_dev = std::min(count, (int)APD_MAX_DEVICES); device_ids = nullptr; }
+    if (n_dev > APD_MAX_DEVICES) return fail(nullptr, APD_ERR_UNSUPPORTED, "more than APD_MAX_DEVICES devices in one group");
+    std::vector<int> ids(n_dev);
+    for (int k = 0; k < n_dev; k++) {
+        ids[k] = device_ids ? device_ids[k] : k;
+        if (ids[k] < 0 || ids[k] >= count) return fail(nullptr, APD_ERR_INVALID, "device id out of range");
+        for (int q = 0; q < k; q++)
+            if (ids[q] == ids[k]) return fail(nullptr, APD_ERR_INVALID, "a device appears twice in device_ids");
+    }
+    // one host thread per device: the primary contexts are created side by side
+    std::vector<apd_ctx*> ms(n_dev, nullptr);
+    std::vector<apd_status> st(n_dev, APD_OK);
+    std::vector<std::string> errs(n_dev);
+    {
+        std::vector<std::thread> th;
+        for (int k = 0; k < n_dev; k++)
+            th.emplace_back([&, k] {
+                st[k] = create_one(ids[k], &ms[k]);
+                if (st[k] != APD_OK) errs[k] = g_create_error;  // thread_local: carry it over
+            });
+        for (auto& x : th) x.join();
+    }
+    for (int k = 0; k < n_dev; k++)
+        if (st[k] != APD_OK) {
+            g_create_error = errs[k];
+            for (apd_ctx* m : ms) destroy_one(m);
+            return st[k];
+        }
+    apd_ctx* L = ms[0];
+    L->members.assign(ms.begin(), ms.end());
+    for (int k = 0; k < n_dev; k++) {
+        ms[k]->lead = L;
+        ms[k]->rank = (uint32_t)k;
+        ms[k]->world = (uint32_t)n_dev;
+        if (k) ms[k]->members.clear();
+    }
+    // Peer mappings: with all of them in place the DTW kernels store their results into every
+    // member's memory (NVLink / NVSwitch); without, the shards are copied after the kernels.
+    bool p2p = true;
+    for (int a = 0; a < n_dev && p2p; a++)
+        for (int b = 0; b < n_dev; b++) {
+            if (a == b) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, ids[a], ids[b]) != cudaSuccess || !can) { p2p = false; break; }
+        }
+    const char* nop2p = getenv("APD_NO_P2P");
+    if (nop2p && nop2p[0] == '1') p2p = false;
+    if (p2p)
+        for (int a = 0; a < n_dev; a++) {
+            cudaSetDevice(ids[a]);
+            for (int b = 0; b < n_dev; b++) {
+                if (a == b) continue;
+                cudaError_t e = cudaDeviceEnablePeerAccess(ids[b], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+                if (e != cudaSuccess) { cudaGetLastError(); p2p = false; }
+            }
+        }
+    L->p2p = p2p && n_dev > 1;
+    cudaSetDevice(L->device);
+    *out = L;
     return APD_OK;
 }
 
 void apd_destroy(apd_ctx* c)
 {
     if (!c) return;
-    cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
-    void* dptrs[] = {c->d_arena, c->d_off, c->d_len, c->d_perm, c->d_srcoff, c->d_raw, c->d_units, c->d_packed,
-                     c->d_matrix, c->d_gstate, c->d_counters, c->d_error, c->d_tiles, c->d_hist};
-    for (void* p : dptrs) if (p) cudaFree(p);
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    cudaEvent_t evs[] = {c->ev_k0, c->ev_k1, c->ev_s0, c->ev_s1, c->ev_h0, c->ev_h1, c->ev_d0, c->ev_d1};
-    for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
-    if (c->stream) cudaStreamDestroy(c->stream);
-    delete c;
+    std::vector<apd_ctx*> ms = c->members;   // copy: destroy_one deletes the leader too
+    if (ms.empty()) { destroy_one(c); return; }
+    for (size_t k = ms.size(); k-- > 0;) destroy_one(ms[k]);
+}
+
+apd_status apd_group_size(apd_ctx* c, uint32_t* n_dev, uint32_t* peer_stores)
+{
+    if (!c || !n_dev) return APD_ERR_INVALID;
+    *n_dev = (uint32_t)c->lead->members.size();
+    if (peer_stores) *peer_stores = c->lead->p2p ? 1u : 0u;
+    return APD_OK;
 }
 
 apd_status apd_set_sequences(apd_ctx* c, const float* const* frames, const uint32_t* lens, uint32_t n, uint32_t dim)
@@ -464,24 +826,19 @@ apd_status apd_set_sequences(apd_ctx* c, const float* const* frames, const uint3
     for (uint32_t k = 0; k < n; k++)
         if (lens[k] > 0 && !frames[k]) return fail(c, APD_ERR_INVALID, "frames[k] is NULL for a non-empty sequence");
     const size_t floats = (size_t)c->arena.total_frames * c->arena.dpad;
-    if (floats > c->stage_cap) {
-        if (c->h_stage) cudaFreeHost(c->h_stage);
-        c->h_stage = nullptr; c->stage_cap = 0;
-        APD_CUDA(c, cudaMallocHost((void**)&c->h_stage, floats * sizeof(float)));
-        c->stage_cap = floats;
-    }
-    // CPU half of the packing glue: sort + pad into the pinned staging buffer.
-    fill_arena(c->arena, frames, c->h_stage);
     APD_CUDA(c, cudaEventRecord(c->ev_h0, c->stream));
-    APD_CUDA(c, cudaMemcpyAsync(c->d_arena, c->h_stage, floats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    // CPU half of the packing glue: sort + pad, piecewise through the pinned ring, overlapped with the H2D copies.
+    s = upload_arena(c, frames);
+    if (s != APD_OK) return s;
     s = upload_tables(c, nullptr);
     if (s != APD_OK) return s;
     APD_CUDA(c, cudaEventRecord(c->ev_h1, c->stream));
     c->timed_h2d = true;
-    c->stats.h2d_bytes = floats * sizeof(float);
-    c->stats.n_sequences = n;
-    c->stats.ordered_pairs = (uint64_t)n * (n ? n - 1 : 0);
-    APD_CUDA(c, cudaStreamSynchronize(c->stream));
+    set_sequence_stats(c, n, floats * sizeof(float));
+    s = broadcast_arena(c);
+    if (s != APD_OK) return s;
+    // The caller's buffers have been copied; the tail of the upload is still in flight on the
+    // context's stream, and everything that follows is ordered behind it.
     c->have_sequences = true;
     return APD_OK;
 }
@@ -503,8 +860,6 @@ apd_status apd_set_sequences_flat(apd_ctx* c, const float* flat, const uint64_t*
         APD_CUDA(c, cudaMemcpyAsync(c->d_raw, flat, extent * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     s = upload_tables(c, src_sorted.data());
     if (s != APD_OK) return s;
-    APD_CUDA(c, cudaEventRecord(c->ev_h1, c->stream));
-    c->timed_h2d = true;
     // Device half of the packing glue: zero the arena (pads), then gather.
     APD_CUDA(c, cudaMemsetAsync(c->d_arena, 0, (size_t)c->arena.total_frames * c->arena.dpad * sizeof(float), c->stream));
     if (n) {
@@ -513,17 +868,113 @@ apd_status apd_set_sequences_flat(apd_ctx* c, const float* flat, const uint64_t*
                                                        c->arena.dpad, c->d_arena);
         APD_CUDA(c, cudaGetLastError());
     }
-    c->stats.h2d_bytes = extent * sizeof(float);
-    c->stats.n_sequences = n;
-    c->stats.ordered_pairs = (uint64_t)n * (n ? n - 1 : 0);
-    APD_CUDA(c, cudaStreamSynchronize(c->stream));  // src_sorted and the caller's buffer may go away
+    APD_CUDA(c, cudaEventRecord(c->ev_h1, c->stream));
+    c->timed_h2d = true;
+    set_sequence_stats(c, n, extent * sizeof(float));
+    s = broadcast_arena(c);
+    if (s != APD_OK) return s;
+    APD_CUDA(c, cudaStreamSynchronize(c->stream));  // src_sorted and the caller's (possibly pageable) buffer may go away
     c->have_sequences = true;
+    return APD_OK;
+}
+
+apd_status apd_set_sequences_encoded(apd_ctx* c, const float* const* cepstra, const uint32_t* lens, uint32_t n,
+                                     uint32_t n_bins, const float* w_encode, const float* b_encode, uint32_t n_latent)
+{
+    if (!c) return APD_ERR_INVALID;
+    if (n_bins == 0 || n_bins > APD_AE_MAX_BINS) return fail(c, APD_ERR_UNSUPPORTED, "n_bins must be 1..APD_AE_MAX_BINS");
+    if (!w_encode || !b_encode) return fail(c, APD_ERR_INVALID, "w_encode/b_encode is NULL");
+    apd_status s = begin_sequences(c, lens, n, n_latent);
+    if (s != APD_OK) return s;
+    if (n > 0 && !cepstra) return fail(c, APD_ERR_INVALID, "cepstra is NULL");
+    for (uint32_t k = 0; k < n; k++)
+        if (lens[k] > 0 && !cepstra[k]) return fail(c, APD_ERR_INVALID, "cepstra[k] is NULL for a non-empty sequence");
+    const Arena& ar = c->arena;
+    // Raw cepstra go up in sorted order, densely (no padding): sequence s starts at src_sorted[s] floats.
+    std::vector<uint64_t> src_sorted(n);
+    uint64_t total_frames = 0;
+    for (uint32_t sidx = 0; sidx < n; sidx++) { src_sorted[sidx] = total_frames * n_bins; total_frames += ar.len[sidx]; }
+    const uint64_t extent = total_frames * n_bins;
+    s = ensure_device(c, c->d_raw, c->raw_cap, (size_t)extent);
+    if (s != APD_OK) return s;
+    const size_t wfloats = (size_t)n_bins * n_latent + n_latent;
+    s = ensure_device(c, c->d_aux, c->aux_cap, wfloats);
+    if (s != APD_OK) return s;
+    s = ensure_stage_ring(c);
+    if (s != APD_OK) return s;
+    APD_CUDA(c, cudaEventRecord(c->ev_h0, c->stream));
+    // weights: one small pageable copy each (staged before the call returns)
+    APD_CUDA(c, cudaMemcpyAsync(c->d_aux, w_encode, (size_t)n_bins * n_latent * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    APD_CUDA(c, cudaMemcpyAsync(c->d_aux + (size_t)n_bins * n_latent, b_encode, n_latent * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    // cepstra through the pinned ring, sequence by sequence in sorted order
+    {
+        const uint64_t buf_floats = kStageBytes / sizeof(float);
+        int b = 0;
+        uint64_t chunk = 0, fill = 0, dst0 = 0;
+        auto flush = [&]() -> apd_status {
+            if (!fill) return APD_OK;
+            APD_CUDA(c, cudaMemcpyAsync(c->d_raw + dst0, c->h_stage[b], fill * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            APD_CUDA(c, cudaEventRecord(c->ev_stage[b], c->stream));
+            dst0 += fill; fill = 0; chunk++; b = (b + 1) % STAGE_BUFS;
+            APD_CUDA(c, cudaEventSynchronize(c->ev_stage[b]));  // the last copy out of the next buffer (if any) is done
+            return APD_OK;
+        };
+        APD_CUDA(c, cudaEventSynchronize(c->ev_stage[0]));
+        for (uint32_t sidx = 0; sidx < n; sidx++) {
+            const float* src = cepstra[ar.perm[sidx]];
+            uint64_t left = (uint64_t)ar.len[sidx] * n_bins;
+            while (left) {
+                const uint64_t take = std::min<uint64_t>(left, buf_floats - fill);
+                std::memcpy(c->h_stage[b] + fill, src, take * sizeof(float));
+                fill += take; src += take; left -= take;
+                if (fill == buf_floats) { s = flush(); if (s != APD_OK) return s; }
+            }
+        }
+        s = flush();
+        if (s != APD_OK) return s;
+    }
+    s = upload_tables(c, src_sorted.data());
+    if (s != APD_OK) return s;
+    APD_CUDA(c, cudaMemsetAsync(c->d_arena, 0, (size_t)ar.total_frames * ar.dpad * sizeof(float), c->stream));
+    if (n) {
+        cudaError_t e = ae_encode_launch(c->d_raw, c->d_srcoff, c->d_off, c->d_len, n, n_bins, n_latent, ar.dpad, c->d_aux,
+                                         c->d_aux + (size_t)n_bins * n_latent, c->d_arena, c->sm_count, c->stream);
+        if (e != cudaSuccess) return fail(c, APD_ERR_CUDA, std::string("ae_encode_kernel: ") + cudaGetErrorString(e));
+    }
+    APD_CUDA(c, cudaEventRecord(c->ev_h1, c->stream));
+    c->timed_h2d = true;
+    set_sequence_stats(c, n, extent * sizeof(float));
+    s = broadcast_arena(c);
+    if (s != APD_OK) return s;
+    APD_CUDA(c, cudaStreamSynchronize(c->stream));  // src_sorted goes out of scope
+    c->have_sequences = true;
+    return APD_OK;
+}
+
+apd_status apd_get_sequence(apd_ctx* c, uint32_t index, float* out, uint64_t cap_floats)
+{
+    if (!c) return APD_ERR_INVALID;
+    if (c->lead != c) return APD_ERR_INVALID;
+    if (!c->have_sequences) return fail(c, APD_ERR_STATE, "apd_set_sequences has not been called");
+    const Arena& ar = c->arena;
+    if (index >= ar.n) return fail(c, APD_ERR_INVALID, "sequence index out of range");
+    uint32_t spos = 0;
+    for (; spos < ar.n; spos++) if (ar.perm[spos] == index) break;
+    const uint64_t need = (uint64_t)ar.len[spos] * ar.dim;
+    if (need > cap_floats) return fail(c, APD_ERR_INVALID, "output buffer too small");
+    if (!need) return APD_OK;
+    if (!out) return fail(c, APD_ERR_INVALID, "out is NULL");
+    APD_CUDA(c, cudaSetDevice(c->device));
+    APD_CUDA(c, cudaMemcpy2DAsync(out, ar.dim * sizeof(float), c->d_arena + (size_t)ar.off[spos] * ar.dpad, ar.dpad * sizeof(float),
+                                  ar.dim * sizeof(float), ar.len[spos], cudaMemcpyDeviceToHost, c->stream));
+    APD_CUDA(c, cudaStreamSynchronize(c->stream));
     return APD_OK;
 }
 
 apd_status apd_set_shard(apd_ctx* c, uint32_t rank, uint32_t world)
 {
     if (!c) return APD_ERR_INVALID;
+    if (grouped(c)) return fail(c, APD_ERR_UNSUPPORTED, "a device group shards internally: apd_set_shard is for one-device contexts");
     if (world == 0 || rank >= world) return fail(c, APD_ERR_INVALID, "need 0 <= rank < world");
     c->rank = rank;
     c->world = world;
@@ -534,6 +985,7 @@ apd_status apd_set_shard(apd_ctx* c, uint32_t rank, uint32_t world)
 apd_status apd_packed_len(apd_ctx* c, const apd_params* p, uint64_t* n_floats)
 {
     if (!c || !n_floats) return APD_ERR_INVALID;
+    if (grouped(c)) return fail(c, APD_ERR_UNSUPPORTED, "device-buffer stages are for one-device contexts");
     if (!c->have_sequences) return fail(c, APD_ERR_STATE, "apd_set_sequences has not been called");
     apd_status s = check_params(c, p);
     if (s != APD_OK) return s;
@@ -547,6 +999,7 @@ apd_status apd_packed_len(apd_ctx* c, const apd_params* p, uint64_t* n_floats)
 apd_status apd_align_packed(apd_ctx* c, const apd_params* p, float* d_packed, void* stream)
 {
     if (!c) return APD_ERR_INVALID;
+    if (grouped(c)) return fail(c, APD_ERR_UNSUPPORTED, "device-buffer stages are for one-device contexts");
     if (!c->have_sequences) return fail(c, APD_ERR_STATE, "apd_set_sequences has not been called");
     apd_status s = check_params(c, p);
     if (s != APD_OK) return s;
@@ -555,18 +1008,21 @@ apd_status apd_align_packed(apd_ctx* c, const apd_params* p, float* d_packed, vo
     s = ensure_plan(c, p->warping_band_percentage);
     if (s != APD_OK) return s;
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    if (st != c->stream) APD_CUDA(c, cudaStreamSynchronize(c->stream));  // plan upload happens on ctx->stream
-    return run_dtw(c, p, d_packed, st);
+    float* outs[1] = {d_packed};
+    return run_dtw(c, p, outs, 1, st);   // ordered behind the uploads on the context's stream by the in-flight guard
 }
 
 apd_status apd_scatter_packed(apd_ctx* c, const float* d_gathered, uint32_t world, float* d_out_nxn, void* stream)
 {
     if (!c) return APD_ERR_INVALID;
+    if (grouped(c)) return fail(c, APD_ERR_UNSUPPORTED, "device-buffer stages are for one-device contexts");
     if (!c->have_sequences || !c->plan_valid) return fail(c, APD_ERR_STATE, "no aligned plan: call apd_align_packed first");
     if (world != c->world && world != 1) return fail(c, APD_ERR_INVALID, "world must equal the shard world (or 1 for this shard only)");
     if (c->arena.n && !d_out_nxn) return fail(c, APD_ERR_INVALID, "d_out_nxn is NULL");
     APD_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    apd_status s = guard_begin(c, st);
+    if (s != APD_OK) return s;
     return run_scatter(c, d_gathered, world, d_out_nxn, st);
 }
 
@@ -574,37 +1030,99 @@ apd_status apd_synchronize(apd_ctx* c, void* stream)
 {
     if (!c) return APD_ERR_INVALID;
     APD_CUDA(c, cudaSetDevice(c->device));
-    return finish(c, stream ? (cudaStream_t)stream : c->stream);
+    apd_status s = finish_member(c, stream ? (cudaStream_t)stream : c->stream);
+    collect_stats(c->lead);
+    return s;
 }
 
 apd_status apd_align_all(apd_ctx* c, const apd_params* p, float* out_nxn)
 {
     if (!c) return APD_ERR_INVALID;
+    if (c->lead != c) return fail(c, APD_ERR_INVALID, "not a context handle returned by apd_create / apd_create_multi");
     if (!c->have_sequences) return fail(c, APD_ERR_STATE, "apd_set_sequences has not been called");
     apd_status s = check_params(c, p);
     if (s != APD_OK) return s;
     const uint64_t N = c->arena.n;
     if (N && !out_nxn) return fail(c, APD_ERR_INVALID, "out_nxn is NULL");
-    APD_CUDA(c, cudaSetDevice(c->device));
+    c->matrix_valid = false;
     s = ensure_plan(c, p->warping_band_percentage);
     if (s != APD_OK) return s;
-    size_t pk = (size_t)packed_entries(c) * 64;
-    s = ensure_device(c, c->d_packed, c->packed_cap, pk);
-    if (s != APD_OK) return s;
-    s = ensure_device(c, c->d_matrix, c->matrix_cap, (size_t)(N * N));
-    if (s != APD_OK) return s;
-    s = run_dtw(c, p, c->d_packed, c->stream);
-    if (s != APD_OK) return s;
-    s = run_scatter(c, c->d_packed, 1, c->d_matrix, c->stream);
-    if (s != APD_OK) return s;
-    APD_CUDA(c, cudaEventRecord(c->ev_d0, c->stream));
-    if (N) APD_CUDA(c, cudaMemcpyAsync(out_nxn, c->d_matrix, N * N * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    APD_CUDA(c, cudaEventRecord(c->ev_d1, c->stream));
-    c->timed_d2h = true;
+    const uint32_t G = (uint32_t)c->members.size();
+    const bool group = G > 1;
+    // A shard of a multi-process job (apd_set_shard) expands only its own units; a group gathers all of them.
+    const uint32_t gather_ranks = group ? G : 1u;
+    const size_t pk = (size_t)packed_entries(c) * 64;   // floats per shard
+    for (apd_ctx* m : c->members) {
+        APD_CUDA(m, cudaSetDevice(m->device));
+        s = guard_begin(m, m->stream);
+        if (s != APD_OK) return s;
+        s = ensure_device(m, m->d_packed, m->packed_cap, pk * gather_ranks);
+        if (s != APD_OK) return s;
+        s = ensure_device(m, m->d_matrix, m->matrix_cap, (size_t)(N * N));
+        if (s != APD_OK) return s;
+    }
+    // DTW kernels on every member; with peer mappings they store into every member's gathered buffer.
+    for (apd_ctx* m : c->members) {
+        APD_CUDA(m, cudaSetDevice(m->device));
+        float* outs[APD_MAX_GROUP];
+        uint32_t n_out = 0;
+        if (group && c->p2p) {
+            for (apd_ctx* q : c->members) outs[n_out++] = q->d_packed + (size_t)m->rank * pk;
+        } else {
+            outs[n_out++] = m->d_packed + (group ? (size_t)m->rank * pk : 0);
+        }
+        s = run_dtw(m, p, outs, n_out, m->stream);
+        if (s != APD_OK) return s;
+        if (group) APD_CUDA(m, cudaEventRecord(m->ev_dtw, m->stream));
+    }
+    // Every member's matrix needs every member's shard.
+    if (group)
+        for (apd_ctx* m : c->members) {
+            APD_CUDA(m, cudaSetDevice(m->device));
+            for (apd_ctx* q : c->members) {
+                if (q == m) continue;
+                APD_CUDA(m, cudaStreamWaitEvent(m->stream, q->ev_dtw, 0));
+                if (!c->p2p)  // no peer mappings: pull q's shard after its kernels
+                    APD_CUDA(m, cudaMemcpyPeerAsync(m->d_packed + (size_t)q->rank * pk, m->device,
+                                                    q->d_packed + (size_t)q->rank * pk, q->device, pk * sizeof(float), m->stream));
+            }
+        }
+    for (apd_ctx* m : c->members) {
+        APD_CUDA(m, cudaSetDevice(m->device));
+        s = run_scatter(m, m->d_packed, gather_ranks, m->d_matrix, m->stream);
+        if (s != APD_OK) return s;
+    }
+    // Device -> host: member g copies rows [g*N/G, (g+1)*N/G) of the matrix it assembled, so a group
+    // uses G PCIe links at once (one host thread per member: the copy into pageable memory blocks).
     c->stats.d2h_bytes = N * N * sizeof(float);
-    s = finish(c, c->stream);
-    c->matrix_valid = (s == APD_OK);
-    return s;
+    std::vector<apd_status> st(G, APD_OK);
+    auto d2h = [&](uint32_t g) {
+        apd_ctx* m = c->members[g];
+        auto body = [&]() -> apd_status {
+            APD_CUDA(m, cudaSetDevice(m->device));
+            const uint64_t r0 = N * g / G, r1 = N * (g + 1) / G;
+            if (m == c) APD_CUDA(m, cudaEventRecord(c->ev_d0, m->stream));
+            if (r1 > r0)
+                APD_CUDA(m, cudaMemcpyAsync(out_nxn + r0 * N, m->d_matrix + r0 * N, (r1 - r0) * N * sizeof(float),
+                                            cudaMemcpyDeviceToHost, m->stream));
+            if (m == c) { APD_CUDA(m, cudaEventRecord(c->ev_d1, m->stream)); c->timed_d2h = true; }
+            return finish_member(m, m->stream);
+        };
+        st[g] = body();
+    };
+    if (!group) {
+        d2h(0);
+    } else {
+        std::vector<std::thread> th;
+        for (uint32_t g = 0; g < G; g++) th.emplace_back(d2h, g);
+        for (auto& x : th) x.join();
+    }
+    APD_CUDA(c, cudaSetDevice(c->device));
+    collect_stats(c);
+    for (uint32_t g = 0; g < G; g++)
+        if (st[g] != APD_OK) { c->err = c->members[g]->err; return st[g]; }
+    c->matrix_valid = true;
+    return APD_OK;
 }
 
 static apd_status align_pairs_impl(apd_ctx* c, const apd_params* p, long long band_override, const uint32_t* pairs_ij,
@@ -612,6 +1130,7 @@ static apd_status align_pairs_impl(apd_ctx* c, const apd_params* p, long long ba
                                    uint64_t* path_lens)
 {
     if (!c) return APD_ERR_INVALID;
+    if (c->lead != c) return APD_ERR_INVALID;
     if (!c->have_sequences) return fail(c, APD_ERR_STATE, "apd_set_sequences has not been called");
     apd_status s = check_params(c, p);
     if (s != APD_OK) return s;
@@ -619,13 +1138,54 @@ static apd_status align_pairs_impl(apd_ctx* c, const apd_params* p, long long ba
     if (!pairs_ij || !scores) return fail(c, APD_ERR_INVALID, "pairs_ij/scores is NULL");
     for (uint64_t k = 0; k < 2 * n_pairs; k++)
         if (pairs_ij[k] >= c->arena.n) return fail(c, APD_ERR_INVALID, "pair index out of range");
-    APD_CUDA(c, cudaSetDevice(c->device));
-    std::string err;
-    cudaError_t e = pair_paths_run(c->arena, c->d_arena, c->d_off, c->d_len, pairs_ij, n_pairs, p->warping_band_percentage,
-                                   band_override, p->insertion_penalty, p->deletion_penalty, p->match_penalty,
-                                   p->mode == APD_MODE_STRICT, scores, paths_ij, path_cap, path_lens, c->stream, err);
-    if (e != cudaSuccess) return fail(c, APD_ERR_CUDA, err.empty() ? cudaGetErrorString(e) : err);
-    if (!err.empty()) return fail(c, APD_ERR_INVALID, err);
+    // Requested pairs are dealt round-robin to the members of a group (every member holds the arena).
+    const uint32_t G = (uint32_t)c->members.size();
+    std::vector<apd_status> st(G, APD_OK);
+    std::vector<float> path_ms(G, 0.f);
+    auto run = [&](uint32_t g) {
+        apd_ctx* m = c->members[g];
+        auto body = [&]() -> apd_status {
+            const uint64_t k0 = n_pairs * g / G, k1 = n_pairs * (g + 1) / G;
+            if (k1 <= k0) return APD_OK;
+            APD_CUDA(m, cudaSetDevice(m->device));
+            apd_status gs = guard_begin(m, m->stream);
+            if (gs != APD_OK) return gs;
+            std::string err;
+            cudaError_t e = pair_paths_run(c->arena, m->d_arena, m->d_off, m->d_len, pairs_ij + 2 * k0, k1 - k0,
+                                           p->warping_band_percentage, band_override, p->insertion_penalty, p->deletion_penalty,
+                                           p->match_penalty, p->mode == APD_MODE_STRICT, scores + k0,
+                                           paths_ij ? paths_ij + k0 * path_cap * 2 : nullptr, path_cap,
+                                           path_lens ? path_lens + k0 : nullptr, m->sm_count, m->stream, &path_ms[g], err);
+            if (e != cudaSuccess) return fail(m, APD_ERR_CUDA, err.empty() ? cudaGetErrorString(e) : err);
+            if (!err.empty()) return fail(m, APD_ERR_INVALID, err);
+            return APD_OK;
+        };
+        st[g] = body();
+    };
+    if (G == 1 || n_pairs < 2 * G) {
+        // a handful of pairs: the leader alone
+        apd_ctx* m = c;
+        APD_CUDA(m, cudaSetDevice(m->device));
+        s = guard_begin(m, m->stream);
+        if (s != APD_OK) return s;
+        std::string err;
+        cudaError_t e = pair_paths_run(c->arena, m->d_arena, m->d_off, m->d_len, pairs_ij, n_pairs, p->warping_band_percentage,
+                                       band_override, p->insertion_penalty, p->deletion_penalty, p->match_penalty,
+                                       p->mode == APD_MODE_STRICT, scores, paths_ij, path_cap, path_lens, m->sm_count, m->stream,
+                                       &path_ms[0], err);
+        if (e != cudaSuccess) return fail(c, APD_ERR_CUDA, err.empty() ? cudaGetErrorString(e) : err);
+        if (!err.empty()) return fail(c, APD_ERR_INVALID, err);
+    } else {
+        std::vector<std::thread> th;
+        for (uint32_t g = 0; g < G; g++) th.emplace_back(run, g);
+        for (auto& x : th) x.join();
+        APD_CUDA(c, cudaSetDevice(c->device));
+        for (uint32_t g = 0; g < G; g++)
+            if (st[g] != APD_OK) { c->err = c->members[g]->err; return st[g]; }
+    }
+    float ms = 0.f;
+    for (float v : path_ms) ms = std::max(ms, v);
+    c->stats.path_ms = ms;
     return APD_OK;
 }
 
@@ -654,9 +1214,11 @@ static apd_status percentile_impl(apd_ctx* c, const float* d_x, uint64_t len, fl
 {
     if (!out) return fail(c, APD_ERR_INVALID, "out is NULL");
     if (len == 0) return fail(c, APD_ERR_INVALID, "percentile of an empty slice: the reference panics (index out of bounds)");
+    apd_status s = guard_begin(c, st);
+    if (s != APD_OK) return s;
     std::string err;
     uint64_t valid = 0;
-    cudaError_t e = percentile_select(d_x, len, perc, c->d_hist, c->sm_count, st, out, &valid, &c->stats.select_ms, err);
+    cudaError_t e = percentile_select(d_x, len, perc, c->d_hist, c->sm_count, st, out, &valid, &c->lead->stats.select_ms, err);
     if (e != cudaSuccess) return fail(c, APD_ERR_CUDA, cudaGetErrorString(e));
     if (!err.empty()) return fail(c, APD_ERR_INVALID, err);
     return APD_OK;
@@ -679,11 +1241,22 @@ apd_status apd_percentile_device(apd_ctx* c, const float* d_x, uint64_t len, flo
     return percentile_impl(c, d_x, len, perc, stream ? (cudaStream_t)stream : c->stream, out);
 }
 
+const char* apd_last_launch_plan(apd_ctx* c)
+{
+    if (!c) return "";
+    // device 0 of the group describes the launch (every member launches the same classes)
+    static thread_local std::string buf;
+    buf = "[" + c->lead->launch_desc + "]";
+    return buf.c_str();
+}
+
 apd_status apd_get_stats(apd_ctx* c, apd_stats* out)
 {
     if (!c || !out) return APD_ERR_INVALID;
     if (c->have_sequences && c->plan_valid && !c->cells_ref_valid) {
-        c->cells_ref = reference_cells(c->arena, c->plan, c->rank, c->world);
+        // a group covers every unit; a multi-process shard only its own
+        const bool group = c->members.size() > 1;
+        c->cells_ref = reference_cells(c->arena, c->plan, group ? 0 : c->rank, group ? 1 : c->world);
         c->cells_ref_valid = true;
     }
     c->stats.cells_reference = c->cells_ref_valid ? c->cells_ref : 0;

@@ -37,6 +37,8 @@
 
 namespace apd {
 
+enum { APD_MAX_GROUP = 8 };  // devices of one single-process group (one 8 x B200 box)
+
 struct KernelArgs {
     const float* arena;
     const uint32_t* off;   // frame offset of frame 0, sorted position
@@ -50,7 +52,14 @@ struct KernelArgs {
     float pct;
     Penalties pen;
     int St;                // ring size in tiles
-    float2* out;           // packed results: out[k * 32 + lane] = (score(a,b), score(b,a))
+    // Packed results: out[q][k * 32 + lane] = (score(a,b), score(b,a)) for q < n_out.  A single
+    // device writes one buffer.  In a single-process device group (apd_create_multi) every
+    // member's kernel stores its results straight into the gathered buffer of EVERY member
+    // through NVLink peer mappings (out[q] = member q's buffer + this member's rank slot): the
+    // all-gather of the packed shards is fused into the kernel epilogue, 8 bytes per pair and
+    // peer, and no collective follows the kernel.
+    float2* out[APD_MAX_GROUP];
+    uint32_t n_out;
     float2* gstate;        // GSTATE: gridDim.x rings of St*4*32 float2
     int* error_flag;       // set to 1 if a unit needs a bigger ring than St (planner bug)
     unsigned long long* tiles_done;  // optional: lane-tiles executed (statistics)
@@ -319,7 +328,9 @@ APD_D void warp_unit_loop(const KernelArgs& a, DevCtx<DPAD, RING>& ctx)
                 s2 = finish_score(acc.y, n, m);
             }
         }
-        a.out[kk * 32 + lane] = make_float2(s1, s2);
+        const float2 res = make_float2(s1, s2);
+#pragma unroll 1
+        for (uint32_t q = 0; q < a.n_out; q++) a.out[q][kk * 32 + lane] = res;
         __syncwarp();
     }
     if (a.tiles_done) {

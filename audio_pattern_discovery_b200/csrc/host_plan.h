@@ -31,6 +31,9 @@ std::string build_arena_layout(const uint32_t* lens, uint32_t n, uint32_t dim, A
 // pointers: frames[s] -> lens[s] * dim floats in the caller's order.
 void fill_arena(const Arena& layout, const float* const* frames, float* dst);
 
+// Frames [F0, F1) of the arena only: dst[0] is the first float of frame F0 (chunked upload).
+void fill_arena_frames(const Arena& layout, const float* const* frames, uint64_t F0, uint64_t F1, float* dst);
+
 // Layout + fill into out.data (used by the host-side emulator).
 std::string build_arena(const float* const* frames, const uint32_t* lens, uint32_t n,
                         uint32_t dim, Arena& out);

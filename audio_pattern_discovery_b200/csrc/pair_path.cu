@@ -132,8 +132,8 @@ struct DevBuf {
 cudaError_t pair_paths_run(const Arena& ar, const float* d_arena, const uint32_t* d_off,
                            const uint32_t* d_len, const uint32_t* pairs_ij, uint64_t n_pairs, float pct,
                            long long band_override, float ins, float del, float mat, bool strict, float* scores,
-                           uint32_t* paths_ij, uint64_t path_cap, uint64_t* path_lens, cudaStream_t stream,
-                           std::string& err)
+                           uint32_t* paths_ij, uint64_t path_cap, uint64_t* path_lens, int sm_count, cudaStream_t stream,
+                           float* ms, std::string& err)
 {
     err.clear();
     if (paths_ij && path_cap == 0) paths_ij = nullptr;

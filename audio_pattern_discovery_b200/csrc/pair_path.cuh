@@ -39,7 +39,7 @@ struct PairJob {
 cudaError_t pair_paths_run(const Arena& arena, const float* d_arena, const uint32_t* d_off,
                            const uint32_t* d_len, const uint32_t* pairs_ij, uint64_t n_pairs, float pct,
                            long long band_override, float ins, float del, float mat, bool strict, float* scores,
-                           uint32_t* paths_ij, uint64_t path_cap, uint64_t* path_lens, cudaStream_t stream,
-                           std::string& err);
+                           uint32_t* paths_ij, uint64_t path_cap, uint64_t* path_lens, int sm_count, cudaStream_t stream,
+                           float* ms, std::string& err);
 
 }  // namespace apd

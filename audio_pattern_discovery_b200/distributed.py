@@ -88,6 +88,38 @@ class ShardedAligner:
         self.ctx.close()
 
 
+class GroupAligner:
+    """ONE process, several GPUs: the drop-in form of the reference's single blocking
+    `workers.align_all(&discover)` (src/main.rs:189-195).  The library owns the group
+    (apd_create_multi): one upload of the arena + NVLink copies, the pair space dealt over
+    the devices, packed results stored peer-to-peer from inside the DTW kernels, the matrix
+    copied back by every device in parallel.  No torch, no process group."""
+
+    def __init__(self, seqs, devices="all", mode=APD_MODE_STRICT):
+        self.mode = mode
+        self.ctx = Context(devices=devices)
+        self.world = self.ctx.group_size
+        self.ctx.set_sequences(seqs)
+        self.n = self.ctx.n
+
+    def set_sequences(self, seqs):
+        self.ctx.set_sequences(seqs)
+        self.n = self.ctx.n
+
+    def align_all(self, pct, ins=1.0, dele=1.0, mat=1.0, out=None):
+        """-> (n, n) float32 host array (any host memory; pageable is fine)."""
+        return self.ctx.align_all(pct, ins, dele, mat, self.mode, out=out)
+
+    def percentile_of_matrix(self, perc):
+        return self.ctx.percentile(perc)
+
+    def stats(self):
+        return self.ctx.stats()
+
+    def close(self):
+        self.ctx.close()
+
+
 def partition_check(n_units, world):
     """Units u with u % world == rank: sizes per rank (host-side helper for tests)."""
     return [len(range(r, n_units, world)) for r in range(world)]

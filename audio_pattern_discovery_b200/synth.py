@@ -41,7 +41,14 @@ def make_sequences(n, lens, dim, k_prototypes, seed, noise=0.1, zscore=False):
 
 # The configurations BASELINE.json names (SURVEY.md section 8 shorthand C2..C5).
 def config(name, n=None):
-    rng_len = np.random.default_rng({"C2": 2002, "C3": 2003, "C4": 2004, "C5": 2005}[name])
+    rng_len = np.random.default_rng({"C2": 2002, "C3": 2003, "C4": 2004, "C5": 2005, "C1ref": 2001}[name])
+    if name == "C1ref":
+        # The reference's own shipped configuration (project/config/Discovery.toml:5,17-20): ~200 slices
+        # of >= vat_min_len = 150 frames, auto-encoder embeddings (dim 10, per-frame z-scored like
+        # src/neural.rs:61-62), warping_band_percentage = 1.0 (effectively unbanded), unit penalties.
+        n = n or 200
+        return dict(n=n, lens=rng_len.integers(150, 261, size=n), dim=10, k=12, seed=1001, pct=1.0,
+                    weights=(1.0, 1.0, 1.0), zscore=True)
     if name == "C2":
         n = n or 2000
         return dict(n=n, lens=rng_len.integers(64, 257, size=n), dim=20, k=40, seed=1002, pct=0.1,

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define APD_ABI_VERSION 1
+#define APD_ABI_VERSION 2
 
 typedef enum {
     APD_OK = 0,
@@ -36,6 +36,8 @@ typedef enum {
 } apd_status;
 
 #define APD_MAX_DIM 32
+#define APD_MAX_DEVICES 8   /* devices of one single-process group (apd_create_multi) */
+#define APD_AE_MAX_BINS 64  /* widest input frame of apd_set_sequences_encoded */
 
 /* Arithmetic variants of the distance kernel. */
 #define APD_MODE_STRICT 0u /* bit-exact with the reference's f32 operation sequence (default) */
@@ -70,7 +72,7 @@ typedef struct {
     float sm_clock_mhz;          /* clock rate the device reports (max), for rooflines */
     uint32_t sm_count;
     float select_ms;             /* radix-select passes of the last apd_percentile_* call */
-    uint32_t reserved;
+    float path_ms;               /* forward + trace-back kernels of the last apd_align_pair(s) call */
 } apd_stats;
 
 /* ---- lifecycle ------------------------------------------------------------ */
@@ -78,6 +80,25 @@ typedef struct {
 /* One context drives one CUDA device.  Replaces AlignmentWorkers::new's role of
  * owning the data (src/alignments.rs:17-26). */
 apd_status apd_create(int device_id, apd_ctx **out);
+
+/* One context that drives n_dev devices of this box from ONE host process -- what the
+ * reference's single blocking call `workers.align_all(&discover)` (src/main.rs:189-195,
+ * src/alignments.rs:31-67: alignment_workers threads in one process) becomes on a multi-GPU
+ * box.  device_ids == NULL: devices 0..n_dev-1; n_dev <= 0: every visible device (at most
+ * APD_MAX_DEVICES).  Every entry point that takes host buffers (apd_set_sequences*,
+ * apd_align_all, apd_align_pair(s), apd_percentile_matrix, apd_get_stats) works on the group:
+ * every device holds the whole sequence arena (one upload, then NVLink copies), computes the
+ * work units u with u % n_dev == its index, and stores its packed results straight into every
+ * other device's gathered buffer through NVLink peer mappings from inside the DTW kernel (the
+ * all-gather is fused into the kernel; without peer access the shards are copied afterwards);
+ * each device expands the matrix and copies its own slab of rows to out_nxn.  The
+ * device-buffer stages (apd_set_shard, apd_packed_len, apd_align_packed, apd_scatter_packed)
+ * belong to the one-process-per-GPU form and return APD_ERR_UNSUPPORTED on a group. */
+apd_status apd_create_multi(const int *device_ids, int n_dev, apd_ctx **out);
+apd_status apd_device_count(int *count); /* visible CUDA devices; APD_ERR_NO_DEVICE if none */
+/* Devices of the context's group (1 for apd_create); *peer_stores (may be NULL) = 1 if the
+ * kernels store into peer memory directly. */
+apd_status apd_group_size(apd_ctx *ctx, uint32_t *n_dev, uint32_t *peer_stores);
 void apd_destroy(apd_ctx *ctx);
 const char *apd_last_error(const apd_ctx *ctx); /* ctx may be NULL: last create error */
 uint32_t apd_abi_version(void);
@@ -94,6 +115,21 @@ apd_status apd_set_sequences(apd_ctx *ctx, const float *const *frames, const uin
 /* Same, from one flat buffer: sequence s starts at flat + offsets[s] (in floats). */
 apd_status apd_set_sequences_flat(apd_ctx *ctx, const float *flat, const uint64_t *offsets,
                                   const uint32_t *lens, uint32_t n, uint32_t dim);
+
+/* The embedding step in front of the path, on the device:
+ * replaces `NDSequence::new(..).encoded(&nn)` of src/main.rs:150-161, i.e.
+ * NDSequence::encoded (src/spectrogram.rs:103-121) = AutoEncoder::predict (src/neural.rs:55-71)
+ * frame by frame: sigmoid(x W + b) * 255, then the per-frame z-score with sigma = max(std, 1.0),
+ * every f32 operation in the reference's order.  cepstra[s] points at lens[s] * n_bins
+ * row-major f32 values (n_bins <= APD_AE_MAX_BINS; 26 in the reference, src/spectrogram.rs:76);
+ * w_encode is n_bins x n_latent row-major (Mat{flat, cols}, src/numerics.rs:169-173), b_encode
+ * n_latent values (n_latent <= APD_MAX_DIM; 10 in project/config/Discovery.toml:5).  The
+ * embeddings are written straight into the arena (frame width n_latent); they never exist on
+ * the host.  apd_get_sequence reads one sequence of the arena back (lens * dim floats). */
+apd_status apd_set_sequences_encoded(apd_ctx *ctx, const float *const *cepstra, const uint32_t *lens,
+                                     uint32_t n, uint32_t n_bins, const float *w_encode,
+                                     const float *b_encode, uint32_t n_latent);
+apd_status apd_get_sequence(apd_ctx *ctx, uint32_t index, float *out, uint64_t cap_floats);
 
 /* Multi-process sharding (one process per GPU, e.g. under torchrun): this
  * context computes work units u with u % world == rank.  Default 0 / 1. */
@@ -119,7 +155,12 @@ apd_status apd_align_all(apd_ctx *ctx, const apd_params *p, float *out_nxn);
  *      world * apd_packed_len floats, rank-major; world == 1 on a sharded context
  *      means "this shard's buffer only") into the device matrix d_out_nxn (n*n
  *      floats, diagonal 0).
- * All work is enqueued on `stream` (a cudaStream_t, 0 = default stream). */
+ * All work is enqueued on `stream` (a cudaStream_t).  stream == 0 / NULL does NOT mean the
+ * legacy default stream: it selects the context's own private non-blocking stream, which has
+ * no implicit ordering with any other stream -- call apd_synchronize(ctx, 0) (or pass your own
+ * stream everywhere) before another stream touches d_packed / d_out_nxn.  Calls on one
+ * context are ordered among themselves whatever streams they name: each one waits (on the
+ * device) for the work the previous one enqueued. */
 apd_status apd_packed_len(apd_ctx *ctx, const apd_params *p, uint64_t *n_floats);
 apd_status apd_align_packed(apd_ctx *ctx, const apd_params *p, float *d_packed, void *stream);
 apd_status apd_scatter_packed(apd_ctx *ctx, const float *d_gathered, uint32_t world,
@@ -190,8 +231,32 @@ apd_status apd_upgma(const float *dist_nxn, uint32_t n, float perc, const float 
                      apd_merge *ops, uint32_t *n_ops, float *threshold_out,
                      uint32_t *assignment_out);
 
+/* ---- persistence (host code) ---------------------------------------------------- */
+
+/* The matrix the reference keeps only in an Arc<Mutex<Vec<f32>>> for the length of learn()
+ * (src/main.rs:194-195), on disk: <stem>.apdm = n*n little-endian f32, row-major, byte for
+ * byte the Vec<f32> handed to clustering() (src/clustering.rs:81-85); <stem>.apdm.json = a
+ * small header {"format": "apd-matrix-1", "n", "dtype": "<f4", "params", "sha256"}.
+ * params_json: a JSON object to store with it (NULL = {}).  apd_load_matrix with
+ * out_nxn == NULL only reports n; verify != 0 checks the payload digest.
+ * Paths (README.md:67 "alignment path information"): <stem>.apdp.json, cells 1-based,
+ * end to start, in the layout apd_align_pairs fills (pair k at paths_ij + k*path_cap*2).
+ * apd_load_paths stores at most cap_pairs entries / path_cap cells each and reports the
+ * full counts in *n_pairs / path_lens.  Errors: apd_last_error(NULL).  Same files as
+ * audio_pattern_discovery_b200/matrix_io.py reads and writes. */
+apd_status apd_save_matrix(const char *stem, const float *dist_nxn, uint32_t n, const char *params_json);
+apd_status apd_load_matrix(const char *stem, float *out_nxn, uint64_t cap_floats, uint32_t *n_out, int verify);
+apd_status apd_save_paths(const char *stem, const uint32_t *pairs_ij, uint64_t n_pairs, const float *scores,
+                          const uint32_t *paths_ij, uint64_t path_cap, const uint64_t *path_lens);
+apd_status apd_load_paths(const char *stem, uint32_t *pairs_ij, float *scores, uint64_t *path_lens,
+                          uint64_t cap_pairs, uint32_t *paths_ij, uint64_t path_cap, uint64_t *n_pairs);
+
 /* ---- introspection --------------------------------------------------------- */
 apd_status apd_get_stats(apd_ctx *ctx, apd_stats *out);
+/* JSON array describing the launch classes of the last DTW enqueue on (the first device of)
+ * this context: where each class keeps its boundary ring (tmem / smem / global), ring height
+ * in tiles, units, grid and residency.  Valid until the next call on this thread. */
+const char *apd_last_launch_plan(apd_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -524,3 +524,52 @@ int apd_oracle_upgma(const float *dist_nxn, uint32_t n, float perc, apd_oracle_m
     free(d.parents); free(assignment); free(roots);
     return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* neural.rs / spectrogram.rs: the embedding step in front of the DTW path    */
+/* ------------------------------------------------------------------------- */
+
+/* AutoEncoder::predict on ONE frame (src/neural.rs:55-71), which is how
+ * NDSequence::encoded calls it (src/spectrogram.rs:103-121: a 1 x n_bins Mat per frame):
+ *   Mat::mul      src/numerics.rs:305-319  flat[j] += x[k] * w[k*cols + j], k ascending from 0.0
+ *                                          (separate multiply and add: Rust never contracts)
+ *   add_col       src/numerics.rs:246-257  += b[j]
+ *   sigmoid       src/numerics.rs:222-232  1.0 / (1.0 + f32::exp(-x))   (libm expf)
+ *   scale(255.0)  src/numerics.rs:296-301
+ *   mean / std    src/numerics.rs:12-29    sequential sums over the n_latent values, /len;
+ *                                          powf(v - mu, 2.0) folds to a product
+ *   sigma = max(std, 1.0); z_score (src/numerics.rs:71-73): (x - mu) / sigma
+ * w_encode is n_bins x n_latent row-major (Mat{flat, cols: n_latent}), b_encode 1 x n_latent. */
+void apd_oracle_ae_predict(const float *x, uint32_t n_bins, const float *w_encode,
+                           const float *b_encode, uint32_t n_latent, float *out)
+{
+    for (uint32_t j = 0; j < n_latent; j++) {
+        float acc = 0.0f;
+        for (uint32_t k = 0; k < n_bins; k++) {
+            float prod = x[k] * w_encode[(size_t)k * n_latent + j];
+            acc += prod;
+        }
+        acc += b_encode[j];
+        float s = 1.0f / (1.0f + expf(-acc));
+        out[j] = s * 255.0f;
+    }
+    float mu = 0.0f;
+    for (uint32_t j = 0; j < n_latent; j++) mu += out[j];
+    mu = mu / (float)n_latent;
+    float sd = 0.0f;
+    for (uint32_t j = 0; j < n_latent; j++) {
+        float t = out[j] - mu;
+        sd += t * t;
+    }
+    sd = sqrtf(sd / (float)n_latent);
+    float sigma = fmaxf(sd, 1.0f); /* f32::max: a NaN std yields 1.0, like fmaxf */
+    for (uint32_t j = 0; j < n_latent; j++) out[j] = (out[j] - mu) / sigma;
+}
+
+/* NDSequence::encoded (src/spectrogram.rs:103-121): predict() frame by frame. */
+void apd_oracle_ae_encode(const float *frames, uint64_t len, uint32_t n_bins, const float *w_encode,
+                          const float *b_encode, uint32_t n_latent, float *out)
+{
+    for (uint64_t t = 0; t < len; t++)
+        apd_oracle_ae_predict(frames + t * n_bins, n_bins, w_encode, b_encode, n_latent, out + t * n_latent);
+}

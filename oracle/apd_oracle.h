@@ -114,6 +114,17 @@ typedef struct {
 int apd_oracle_upgma(const float *dist_nxn, uint32_t n, float perc, apd_oracle_merge *ops,
                      uint32_t *n_ops, float *threshold_out, uint32_t *assignment_out);
 
+/*
+ * AutoEncoder::predict on one frame (src/neural.rs:55-71) and NDSequence::encoded
+ * (src/spectrogram.rs:103-121): the step that produces the reference's real DTW input
+ * (SURVEY.md section 8 row f3).  w_encode: n_bins x n_latent row-major, b_encode: n_latent.
+ * f32::exp is the C library's expf, as in a Rust build on this platform.
+ */
+void apd_oracle_ae_predict(const float *x, uint32_t n_bins, const float *w_encode,
+                           const float *b_encode, uint32_t n_latent, float *out);
+void apd_oracle_ae_encode(const float *frames, uint64_t len, uint32_t n_bins, const float *w_encode,
+                          const float *b_encode, uint32_t n_latent, float *out);
+
 #ifdef __cplusplus
 }
 #endif

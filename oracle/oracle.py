@@ -66,6 +66,8 @@ def lib():
         L.apd_oracle_percentile.argtypes = [fp, C.c_uint64, C.c_float, fp]
         L.apd_oracle_upgma.restype = C.c_int
         L.apd_oracle_upgma.argtypes = [fp, C.c_uint32, C.c_float, C.POINTER(Merge), u32p, fp, u32p]
+        L.apd_oracle_ae_encode.restype = None
+        L.apd_oracle_ae_encode.argtypes = [fp, C.c_uint64, C.c_uint32, fp, fp, C.c_uint32, fp]
         _lib = L
     return _lib
 
@@ -181,3 +183,16 @@ def upgma(dist, perc):
     merges = [(o.merge_i, o.merge_j, o.into, np.float32(o.distance), int(o.tie))
               for o in ops[:n_ops.value]]
     return merges, np.float32(thr.value), assign[:n].copy()
+
+
+def ae_encode(frames, w_encode, b_encode):
+    """NDSequence::encoded (src/spectrogram.rs:103-121) with AutoEncoder::predict per frame
+    (src/neural.rs:55-71): (T, n_bins) -> (T, n_latent) float32."""
+    x = _seq(frames)
+    w = np.ascontiguousarray(w_encode, dtype=np.float32)
+    b = np.ascontiguousarray(b_encode, dtype=np.float32).ravel()
+    n_bins, n_latent = w.shape
+    assert x.shape[1] == n_bins and b.size == n_latent
+    out = np.zeros((x.shape[0], n_latent), dtype=np.float32)
+    lib().apd_oracle_ae_encode(_fp(x), x.shape[0], n_bins, _fp(w), _fp(b), n_latent, _fp(out))
+    return out

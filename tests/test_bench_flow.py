@@ -82,7 +82,8 @@ class StubAligner:
 
     def stats(self):
         return {"cells_reference": 1000 * (self.rank + 1), "kernel_ms": 1.0, "scatter_ms": 0.1, "kernel_launches": 2,
-                "sm_count": 148, "h2d_bytes": 10, "select_ms": 0.5, "units_local": 1, "units_total": 2}
+                "sm_count": 148, "h2d_bytes": 10, "select_ms": 0.5, "units_local": 1, "units_total": 2,
+                "cells_computed": 1100 * (self.rank + 1)}
 
     def close(self):
         pass
@@ -140,3 +141,4 @@ def test_all_ranks_walk_the_same_collectives(world, workload):
     assert d["reference_cells"] == 1000 * world * (world + 1) // 2   # summed over ranks
     assert d["e2e"]["value"] > 0 and d["other_mode"]["gcups"] > 0 and d["threshold_select"]["threshold"] == 1.0
     assert d["gpu_launches"] > 0
+    assert len(d["matrix_checksum_u64"]) == 16 and d["parity_checked"] == 256 and d["e2e_cold"]["value"] > 0
