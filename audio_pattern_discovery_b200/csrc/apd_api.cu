@@ -85,6 +85,7 @@ struct apd_ctx {
     DevStatus* d_status = nullptr;
     DevStatus* h_status = nullptr;                       // pinned
     unsigned long long* d_hist = nullptr;                // 256 radix-select counters
+    PathScratch path_scratch;                            // trace-back scratch (apd_align_pair(s)), grow-only
 
     cudaStream_t class_stream[MAX_CLASSES] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_CLASSES] = {nullptr, nullptr, nullptr, nullptr};
@@ -652,6 +653,7 @@ void destroy_one(apd_ctx* c)
     void* dptrs[] = {c->d_arena, c->d_off, c->d_len, c->d_perm, c->d_srcoff, c->d_raw, c->d_aux, c->d_units, c->d_packed,
                      c->d_matrix, c->d_gstate, c->d_counters, c->d_status, c->d_hist};
     for (void* p : dptrs) if (p) cudaFree(p);
+    c->path_scratch.release();
     if (c->h_status) cudaFreeHost(c->h_status);
     for (int b = 0; b < STAGE_BUFS; b++) {
         if (c->h_stage_raw[b]) { cudaHostUnregister(c->h_stage_raw[b]); free(c->h_stage_raw[b]); }
@@ -1155,7 +1157,7 @@ static apd_status align_pairs_impl(apd_ctx* c, const apd_params* p, long long ba
                                            p->warping_band_percentage, band_override, p->insertion_penalty, p->deletion_penalty,
                                            p->match_penalty, p->mode == APD_MODE_STRICT, scores + k0,
                                            paths_ij ? paths_ij + k0 * path_cap * 2 : nullptr, path_cap,
-                                           path_lens ? path_lens + k0 : nullptr, m->sm_count, m->stream, &path_ms[g], err);
+                                           path_lens ? path_lens + k0 : nullptr, m->sm_count, m->stream, m->path_scratch, &path_ms[g], err);
             if (e != cudaSuccess) return fail(m, APD_ERR_CUDA, err.empty() ? cudaGetErrorString(e) : err);
             if (!err.empty()) return fail(m, APD_ERR_INVALID, err);
             return APD_OK;
@@ -1172,7 +1174,7 @@ static apd_status align_pairs_impl(apd_ctx* c, const apd_params* p, long long ba
         cudaError_t e = pair_paths_run(c->arena, m->d_arena, m->d_off, m->d_len, pairs_ij, n_pairs, p->warping_band_percentage,
                                        band_override, p->insertion_penalty, p->deletion_penalty, p->match_penalty,
                                        p->mode == APD_MODE_STRICT, scores, paths_ij, path_cap, path_lens, m->sm_count, m->stream,
-                                       &path_ms[0], err);
+                                       m->path_scratch, &path_ms[0], err);
         if (e != cudaSuccess) return fail(c, APD_ERR_CUDA, err.empty() ? cudaGetErrorString(e) : err);
         if (!err.empty()) return fail(c, APD_ERR_INVALID, err);
     } else {

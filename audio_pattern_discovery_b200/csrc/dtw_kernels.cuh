@@ -305,8 +305,14 @@ APD_D void warp_unit_loop(const KernelArgs& a, DevCtx<DPAD, RING>& ctx)
         const bool exists = (b > un.a) && (b < a.N);
         const int n = (int)a.len[un.a];
         const int m = exists ? (int)a.len[b] : 0;
-        ctx.rg = row_geometry(n);
         ctx.lg = lane_geometry(exists, n, m, a.pct);
+        {   // the row grid that costs the fewest tiles for most of the warp's lanes (dtw_core.h: choose_rho)
+            const unsigned int v = lane_rho_votes(ctx.lg, n);
+            unsigned int votes = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) votes |= (unsigned int)__popc(__ballot_sync(0xffffffffu, (v >> r) & 1u)) << (8 * r);
+            ctx.rg = row_geometry(n, choose_rho(votes, n));
+        }
         const int Jt_max = __reduce_max_sync(0xffffffffu, ctx.lg.Jt);
         const int wmax = __reduce_max_sync(0xffffffffu, ctx.lg.active ? ctx.lg.w : 0);
         float s1 = APD_INF, s2 = APD_INF;  // an empty side scores +INF (src/alignments.rs:116-125)

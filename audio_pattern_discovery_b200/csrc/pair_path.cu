@@ -1,210 +1,432 @@
-// pair_path.cu -- host runner of the on-device DTW trace-back kernel (pair_path.cuh).
+// pair_path.cu -- K2, the on-device DTW trace-back for requested pairs: kernels and host runner
+// (design notes in pair_path.cuh).
 #include "pair_path.cuh"
 
 #include <algorithm>
+#include <numeric>
 
 namespace apd {
 
 namespace {
 
-// Cells of anti-diagonal t (i + j = t) inside rows 1..n', columns 1..m' and the band
-// j - i in [-w, w-1] (src/alignments.rs:174-175): i in [lo, hi].
-__device__ __forceinline__ void diag_range(int t, int np, int mp, int w, int& lo, int& hi)
-{
-    // j = t - i;  j - i = t - 2i in [-w, w-1]  <=>  i in [ceil((t-w+1)/2), floor((t+w)/2)]
-    int a = t - w + 1;
-    lo = (a >= 0) ? (a + 1) >> 1 : -((-a) >> 1);
-    hi = (t + w) >> 1;
-    if (lo < 1) lo = 1;
-    if (lo < t - mp) lo = t - mp;
-    if (hi > np) hi = np;
-    if (hi > t - 1) hi = t - 1;
-}
-
-__device__ __forceinline__ float pair_distance(const float* __restrict__ x, const float* __restrict__ y,
-                                               int dpad, bool strict)
-{
-    if (strict) {
-        float acc = 0.0f;
-        for (int k = 0; k < dpad; k++) {
-            float d = __fadd_rn(x[k], -y[k]);
-            acc = __fadd_rn(acc, __fmul_rn(d, d));
-        }
-        return __fsqrt_rn(acc);
-    }
-    // Same association as the FAST A stage of row_step(): even / odd partial sums with FMAs.
-    float a0 = 0.0f, a1 = 0.0f;
-    for (int k = 0; k < dpad; k += 2) {
-        float d0 = x[k] - y[k], d1 = x[k + 1] - y[k + 1];
-        a0 = (k == 0) ? __fmul_rn(d0, d0) : __fmaf_rn(d0, d0, a0);
-        a1 = (k == 0) ? __fmul_rn(d1, d1) : __fmaf_rn(d1, d1, a1);
-    }
-    return sqrt_fast(a0 + a1);
-}
-
-__global__ void __launch_bounds__(256) pair_path_kernel(
-    const float* __restrict__ arena, const uint32_t* __restrict__ off, const uint32_t* __restrict__ len,
-    const PairJob* __restrict__ jobs, int dpad, float pct, long long band_override, float pins, float pdel,
-    float pmat, int strict,
-    uint8_t* __restrict__ dirs, float* __restrict__ scores, uint32_t* __restrict__ paths, uint64_t path_cap,
-    unsigned long long* __restrict__ path_lens)
-{
-    extern __shared__ float diag_smem[];
-    const PairJob job = jobs[blockIdx.x];
-    const int n = (int)len[job.xs], m = (int)len[job.ys];
-    const int np = n - 1, mp = m - 1;
-    if (threadIdx.x == 0) path_lens[blockIdx.x] = 0;
-    if (n < 1 || m < 1 || np == 0 || mp == 0) {
-        // src/alignments.rs:116-125: the score cell (n-1, m-1) is the seed (0,0) when
-        // n == m == 1 (0 / 2 = 0) and absent (+INF) when only one side has length 1 or
-        // a side is empty.  No path in either case.
-        if (threadIdx.x == 0) scores[blockIdx.x] = (n == 1 && m == 1) ? 0.0f : APD_INF;
-        return;
-    }
-    const int w = (band_override >= 0) ? window_of_band(band_override, n, m) : window_of(pct, n, m);
-    const float* x0 = arena + (size_t)off[job.xs] * dpad;
-    const float* y0 = arena + (size_t)off[job.ys] * dpad;
-    uint8_t* dir = dirs + job.dir_off;
-    const int L = np + 2;  // diagonals are indexed by i in 0..np
-    float* d0 = diag_smem;          // t-2
-    float* d1 = diag_smem + L;      // t-1
-    float* d2 = diag_smem + 2 * L;  // t
-    for (int i = threadIdx.x; i < L; i += blockDim.x) { d0[i] = APD_INF; d1[i] = APD_INF; d2[i] = APD_INF; }
-    __syncthreads();
-    if (threadIdx.x == 0) d0[0] = 0.0f;  // t = 0: the seed (0,0) = 0 (src/alignments.rs:107-111)
-    __syncthreads();
-    // t = 1 holds only boundary cells (0,1) and (1,0): absent -> d1 stays +INF.
-    for (int t = 2; t <= np + mp; t++) {
-        int lo, hi;
-        diag_range(t, np, mp, w, lo, hi);
-        // Entries of d2 outside [lo, hi] must read as +INF two diagonals later; the band
-        // moves by at most one row per diagonal, so clearing a margin of 2 suffices.
-        for (int i = lo - 2 + (int)threadIdx.x; i <= hi + 2; i += blockDim.x)
-            if (i >= 0 && i < L && (i < lo || i > hi)) d2[i] = APD_INF;
-        for (int i = lo + (int)threadIdx.x; i <= hi; i += blockDim.x) {
-            const int j = t - i;
-            const float dist = pair_distance(x0 + (size_t)(i - 1) * dpad, y0 + (size_t)(j - 1) * dpad, dpad, strict != 0);
-            const float M = d0[i - 1];  // (i-1, j-1)
-            const float I = d1[i - 1];  // (i-1, j)   insertion
-            const float E = d1[i];      // (i, j-1)   deletion
-            // src/alignments.rs:153-159
-            int b = 0;
-            if (E < M && E < I) b = 2;
-            else if (I < M && I < E) b = 1;
-            const float base = (b == 2) ? E : (b == 1 ? I : M);
-            const float pen = (b == 2) ? pdel : (b == 1 ? pins : pmat);
-            d2[i] = __fadd_rn(base, __fmul_rn(pen, dist));
-            dir[(size_t)t * job.stride + (i - lo)] = (uint8_t)b;
-        }
-        __syncthreads();
-        float* tmp = d0; d0 = d1; d1 = d2; d2 = tmp;
-    }
-    // After the rotation d1 holds diagonal np+mp, whose cell i = np is (n', m').
-    if (threadIdx.x == 0) {
-        const float acc = d1[np];
-        scores[blockIdx.x] = finish_score(acc, n, m);
-        unsigned long long plen = 0;
-        int i = np, j = mp;
-        uint32_t* out = paths ? paths + (size_t)blockIdx.x * path_cap * 2 : nullptr;
-        while (i >= 1 && j >= 1) {
-            if (out && plen < path_cap) { out[2 * plen] = (uint32_t)i; out[2 * plen + 1] = (uint32_t)j; }
-            plen++;
-            int lo, hi;
-            const int t = i + j;
-            diag_range(t, np, mp, w, lo, hi);
-            const int b = dir[(size_t)t * job.stride + (i - lo)];
-            if (b == 2) j -= 1;
-            else if (b == 1) i -= 1;
-            else { i -= 1; j -= 1; }
-        }
-        path_lens[blockIdx.x] = plen;
-    }
-}
-
-
-struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, std::max<size_t>(bytes, 1)); }
+struct WaveArgs {
+    const float* arena;
+    const uint32_t* off;
+    const uint32_t* len;
+    const PairJob* jobs;
+    const uint32_t* order;   // job indices, most expensive first (the warps' fetch order)
+    uint32_t n_jobs;
+    unsigned int* counter;
+    float pins, pdel, pmat;
+    uint32_t* scratch;       // direction words (uint32) and slab-link rows (float) live in one buffer
+    float* scores;           // indexed by job
 };
+
+// src/numerics.rs:114-120 for one cell.  STRICT: packed subtract and square, sequential f32
+// accumulation in dimension order, IEEE sqrt -- the same bits as K1 and the reference.  FAST:
+// the association of K1's FAST A stage (even / odd partial sums with FMAs, approximate sqrt).
+template <int DPAD, bool STRICT>
+__device__ __forceinline__ float cell_distance(const F2 (&x)[DPAD / 2], const F2 (&y)[DPAD / 2])
+{
+    if (STRICT) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DPAD / 2; k++) {
+            const F2 t = sub2_rn(x[k], y[k]);
+            const F2 p = mul2_rn(t, t);
+            acc = (k == 0) ? p.x : add_rn(acc, p.x);
+            acc = add_rn(acc, p.y);
+        }
+        return sqrt_rn(acc);
+    }
+    F2 acc2 = mk2(0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < DPAD / 2; k++) {
+        const F2 t = sub2_rn(x[k], y[k]);
+        acc2 = (k == 0) ? mul2_rn(t, t) : fma2_rn(t, t, acc2);
+    }
+    return sqrt_fast(acc2.x + acc2.y);
+}
+
+template <int DPAD, bool STRICT>
+__global__ void __launch_bounds__(32 * PW_WARPS) pair_wave_kernel(const WaveArgs a)
+{
+    extern __shared__ float4 smem4[];
+    constexpr int TS = DPAD + 1;  // float4 per staged y tile: 4 frames (DPAD float4) + 1 pad -> conflict-free LDS.128
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float4* ring = smem4 + warp * (PW_YRING * TS);
+    const uint32_t ring_smem = (uint32_t)__cvta_generic_to_shared(ring);
+    const float INF = APD_INF;
+
+    for (;;) {
+        unsigned int q = 0;
+        if (lane == 0) q = atomicAdd(a.counter, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= a.n_jobs) break;
+        const uint32_t ji = a.order[q];
+        const PairJob jb = a.jobs[ji];
+        const int n = (int)a.len[jb.xs], m = (int)a.len[jb.ys];
+        const int np = n - 1, mp = m - 1, w = jb.w;      // the host only queues pairs with np >= 1 and mp >= 1
+        const float4* xbase4 = reinterpret_cast<const float4*>(a.arena) + (size_t)a.off[jb.xs] * (DPAD / 4);
+        const float4* ybase4 = reinterpret_cast<const float4*>(a.arena) + (size_t)a.off[jb.ys] * (DPAD / 4);
+        uint32_t* dir = a.scratch + jb.dir_off;
+        float* rb = reinterpret_cast<float*>(a.scratch) + jb.row_off;   // rb[j - 1]: last row of the previous slab at column j
+        const int Jt = (mp + 3) >> 2;
+        for (int j = lane; j < 4 * Jt; j += 32) rb[j] = INF;            // row 0 of the DP: absent cells
+        __syncwarp();
+
+        // the score cell (n', m') (src/alignments.rs:116-125)
+        const int kstar = (np - 1) >> 7, lstar = ((np - 1) & 127) >> 2, rstar = (np - 1) & 3;
+        const int Jstar = (mp - 1) >> 2, cstar = (mp - 1) & 3;
+        float ans = INF;
+
+        const int n_slabs = (np + PW_SLAB_ROWS - 1) / PW_SLAB_ROWS;
+        for (int k = 0; k < n_slabs; k++) {
+            int Jlo, Jhi;
+            pw_slab_range(k, np, mp, w, Jlo, Jhi);
+            if (Jhi < Jlo) continue;
+            const int i0 = PW_SLAB_ROWS * k + 1 + 4 * lane;   // first DP row of this lane
+            const bool has_rows = i0 <= np;
+            // x frames of rows i0 .. i0+3 (frame i - 1), clamped to the last row used
+            F2 xr[TILE][DPAD / 2];
+#pragma unroll
+            for (int r = 0; r < TILE; r++) {
+                int i = i0 + r;
+                if (i > np) i = np;
+                const float4* p = xbase4 + (size_t)(i - 1) * (DPAD / 4);
+#pragma unroll
+                for (int v = 0; v < DPAD / 4; v++) {
+                    const float4 f = __ldg(p + v);
+                    xr[r][2 * v] = make_float2(f.x, f.y);
+                    xr[r][2 * v + 1] = make_float2(f.z, f.w);
+                }
+            }
+            float left[TILE], bottom[TILE];
+#pragma unroll
+            for (int r = 0; r < TILE; r++) { left[r] = INF; bottom[r] = INF; }
+            // cell above-left of the lane's first tile: out of band for every lane but the first, whose
+            // upper neighbour row belongs to the previous slab (or is row 0 with the seed (0,0) = 0)
+            float diag = INF;
+            if (lane == 0) diag = (Jlo == 0) ? (k == 0 ? 0.0f : INF) : rb[4 * Jlo - 1];
+
+            auto y_fetch = [&](int J) {
+                if (J <= Jhi && lane < DPAD) {
+                    const uint32_t dst = ring_smem + (uint32_t)(((J & (PW_YRING - 1)) * TS + lane) * 16);
+                    const float4* src = ybase4 + (size_t)J * DPAD + lane;   // frames 4J .. 4J+3 are contiguous
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+                }
+                asm volatile("cp.async.commit_group;");
+            };
+            __syncwarp();   // every lane is done with the ring of the previous slab
+#pragma unroll 1
+            for (int t = 0; t < PW_YLOOK; t++) y_fetch(Jlo + t);
+
+#pragma unroll 1
+            for (int s = Jlo; s <= Jhi + 31; s++) {
+                y_fetch(s + PW_YLOOK);
+                const int J = s - lane;
+                const bool act = has_rows && J >= Jlo && J <= Jhi;
+                // row above the tile: the upper neighbour's bottom row of the previous step; lane 0: the slab link
+                float top[TILE];
+#pragma unroll
+                for (int c = 0; c < TILE; c++) top[c] = __shfl_up_sync(0xffffffffu, bottom[c], 1);
+                if (lane == 0) {
+                    if (act) {
+                        const float4 v = *reinterpret_cast<const float4*>(rb + 4 * J);
+                        top[0] = v.x; top[1] = v.y; top[2] = v.z; top[3] = v.w;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < TILE; c++) top[c] = INF;
+                    }
+                }
+                asm volatile("cp.async.wait_group %0;" ::"n"((int)PW_YLOOK + 0) : "memory");
+                __syncwarp();
+                uint32_t word = 0;
+                if (act) {
+                    const float4* yt = ring + (J & (PW_YRING - 1)) * TS;
+                    const int j0 = 4 * J + 1;
+                    // cell (r, c) is a real in-band cell iff r <= rmax, c <= cmax and dlo <= c - r <= dhi
+                    const int rmax = np - i0, cmax = mp - j0;
+                    const int dlo = -w - (j0 - i0), dhi = (w - 1) - (j0 - i0);
+                    const bool cap = (k == kstar) && (lane == lstar) && (J == Jstar);
+                    float colprev[TILE];
+#pragma unroll
+                    for (int r = 0; r < TILE; r++) colprev[r] = left[r];
+#pragma unroll
+                    for (int c = 0; c < TILE; c++) {
+                        F2 yv[DPAD / 2];
+#pragma unroll
+                        for (int v = 0; v < DPAD / 4; v++) {
+                            const float4 f = yt[c * (DPAD / 4) + v];
+                            yv[2 * v] = make_float2(f.x, f.y);
+                            yv[2 * v + 1] = make_float2(f.z, f.w);
+                        }
+                        float up = top[c];
+                        float dg = (c == 0) ? diag : top[c - 1];
+#pragma unroll
+                        for (int r = 0; r < TILE; r++) {
+                            const float d = cell_distance<DPAD, STRICT>(xr[r], yv);
+                            const float E = colprev[r];   // (i, j-1)   deletion
+                            const float I = up;           // (i-1, j)   insertion
+                            const float M = dg;           // (i-1, j-1) match
+                            // src/alignments.rs:153-159
+                            uint32_t b = 0;
+                            if (E < M && E < I) b = 2;
+                            else if (I < M && I < E) b = 1;
+                            const float base = (b == 2) ? E : (b == 1 ? I : M);
+                            const float pen = (b == 2) ? a.pdel : (b == 1 ? a.pins : a.pmat);
+                            float v = add_rn(base, mul_rn(pen, d));
+                            const bool ok = (r <= rmax) && (c <= cmax) && (c - r >= dlo) && (c - r <= dhi);
+                            v = ok ? v : INF;             // what a missing map entry reads as
+                            b = ok ? b : 0u;
+                            word |= b << (2 * (4 * r + c));
+                            if (cap && r == rstar && c == cstar) ans = v;
+                            dg = colprev[r];
+                            colprev[r] = v;
+                            up = v;
+                        }
+                        bottom[c] = up;
+                    }
+#pragma unroll
+                    for (int r = 0; r < TILE; r++) left[r] = colprev[r];
+                    dir[((size_t)k * jb.steps_max + (size_t)(s - Jlo)) * 32 + lane] = word;
+                    if (lane == 31) *reinterpret_cast<float4*>(rb + 4 * J) = make_float4(bottom[0], bottom[1], bottom[2], bottom[3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < TILE; c++) bottom[c] = INF;
+                }
+                diag = top[TILE - 1];
+            }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();   // lane 31's slab-link row is visible to lane 0 of the next slab
+        }
+        // one lane holds the score cell
+        const float got = __shfl_sync(0xffffffffu, ans, lstar);
+        if (lane == 0) a.scores[ji] = finish_score(got, n, m);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(64) pair_trace_kernel(const PairJob* __restrict__ jobs, uint32_t n_jobs,
+                                                        const uint32_t* __restrict__ len, const uint32_t* __restrict__ scratch,
+                                                        uint32_t* __restrict__ paths, uint64_t path_cap,
+                                                        unsigned long long* __restrict__ path_lens)
+{
+    const uint32_t ji = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ji >= n_jobs) return;
+    const PairJob jb = jobs[ji];
+    const int np = (int)len[jb.xs] - 1, mp = (int)len[jb.ys] - 1, w = jb.w;
+    const uint32_t* dir = scratch + jb.dir_off;
+    uint32_t* out = paths ? paths + (size_t)ji * path_cap * 2 : nullptr;
+    unsigned long long plen = 0;
+    int i = np, j = mp, kc = -1, Jlo = 0, Jhi = -1;
+    while (i >= 1 && j >= 1) {
+        if (out && plen < path_cap) { out[2 * plen] = (uint32_t)i; out[2 * plen + 1] = (uint32_t)j; }
+        plen++;
+        const int k = (i - 1) >> 7, l = ((i - 1) & 127) >> 2, r = (i - 1) & 3, J = (j - 1) >> 2, c = (j - 1) & 3;
+        if (k != kc) { pw_slab_range(k, np, mp, w, Jlo, Jhi); kc = k; }
+        uint32_t b = 0;   // a cell outside the band reads as a missing map entry everywhere: MATCH
+        if (J >= Jlo && J <= Jhi) {
+            const uint32_t word = dir[((size_t)k * jb.steps_max + (size_t)(J + l - Jlo)) * 32 + l];
+            b = (word >> (2 * (4 * r + c))) & 3u;
+        }
+        if (b == 2) j -= 1;
+        else if (b == 1) i -= 1;
+        else { i -= 1; j -= 1; }
+    }
+    path_lens[ji] = plen;
+}
+
+template <int DPAD>
+cudaError_t launch_wave(const WaveArgs& a, bool strict, int grid, cudaStream_t stream)
+{
+    const size_t smem = (size_t)PW_WARPS * PW_YRING * (DPAD + 1) * sizeof(float4);
+    cudaError_t e;
+    if (strict) {
+        e = cudaFuncSetAttribute(pair_wave_kernel<DPAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        pair_wave_kernel<DPAD, true><<<grid, 32 * PW_WARPS, smem, stream>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(pair_wave_kernel<DPAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        pair_wave_kernel<DPAD, false><<<grid, 32 * PW_WARPS, smem, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wave_dpad(uint32_t dpad, const WaveArgs& a, bool strict, int grid, cudaStream_t stream)
+{
+    switch (dpad) {
+        case 4: return launch_wave<4>(a, strict, grid, stream);
+        case 8: return launch_wave<8>(a, strict, grid, stream);
+        case 12: return launch_wave<12>(a, strict, grid, stream);
+        case 16: return launch_wave<16>(a, strict, grid, stream);
+        case 20: return launch_wave<20>(a, strict, grid, stream);
+        case 24: return launch_wave<24>(a, strict, grid, stream);
+        case 28: return launch_wave<28>(a, strict, grid, stream);
+        case 32: return launch_wave<32>(a, strict, grid, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <class T>
+cudaError_t grow(T*& p, size_t& cap, size_t need_bytes)
+{
+    if (p && cap >= need_bytes) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    need_bytes = std::max<size_t>(need_bytes, 256);
+    cudaError_t e = cudaMalloc((void**)&p, need_bytes);
+    if (e == cudaSuccess) cap = need_bytes;
+    return e;
+}
+
 }  // namespace
+
+void PathScratch::release()
+{
+    if (d_buf) cudaFree(d_buf);
+    if (d_jobs) cudaFree(d_jobs);
+    if (d_scores) cudaFree(d_scores);
+    if (d_lens) cudaFree(d_lens);
+    if (d_paths) cudaFree(d_paths);
+    if (d_counter) cudaFree(d_counter);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    *this = PathScratch();
+}
 
 cudaError_t pair_paths_run(const Arena& ar, const float* d_arena, const uint32_t* d_off,
                            const uint32_t* d_len, const uint32_t* pairs_ij, uint64_t n_pairs, float pct,
                            long long band_override, float ins, float del, float mat, bool strict, float* scores,
                            uint32_t* paths_ij, uint64_t path_cap, uint64_t* path_lens, int sm_count, cudaStream_t stream,
-                           float* ms, std::string& err)
+                           PathScratch& sc, float* ms, std::string& err)
 {
     err.clear();
+    if (ms) *ms = 0.f;
     if (paths_ij && path_cap == 0) paths_ij = nullptr;
     std::vector<uint32_t> inv(ar.n);
     for (uint32_t s = 0; s < ar.n; s++) inv[ar.perm[s]] = s;
-
-    int dev = 0, smem_optin = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (e != cudaSuccess) return e;
+    cudaError_t e;
+    if (!sc.ev0) {
+        if ((e = cudaEventCreate(&sc.ev0)) != cudaSuccess) return e;
+        if ((e = cudaEventCreate(&sc.ev1)) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void**)&sc.d_counter, sizeof(unsigned int))) != cudaSuccess) return e;
+    }
     size_t free_b = 0, total_b = 0;
-    e = cudaMemGetInfo(&free_b, &total_b);
-    if (e != cudaSuccess) return e;
-    const uint64_t budget = std::max<uint64_t>(std::min<uint64_t>(free_b / 2, 8ull << 30), 64ull << 20);
+    if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return e;
+    // direction scratch budget: what is free now plus what this context already holds for it
+    const uint64_t budget = std::max<uint64_t>(std::min<uint64_t>((free_b + sc.cap) / 2, 64ull << 30), 64ull << 20);
 
     uint64_t done = 0;
     while (done < n_pairs) {
-        // Greedy chunk: as many pairs as fit the scratch budget (at least one).
+        // Greedy chunk in request order: as many pairs as fit the scratch budget (at least one).
         std::vector<PairJob> jobs;
-        uint64_t dir_bytes = 0;
-        size_t smem_max = 0;
+        std::vector<uint32_t> job_req;      // request index (relative to `done`) of each job
+        std::vector<uint64_t> cost;
+        uint64_t words = 0;                 // scratch cursor, in 4-byte units
         uint64_t k = done;
         for (; k < n_pairs; k++) {
-            PairJob j;
+            PairJob j{};
             j.xs = inv[pairs_ij[2 * k]];
             j.ys = inv[pairs_ij[2 * k + 1]];
+            j.out = (uint32_t)(k - done);
             const int n = (int)ar.len[j.xs], m = (int)ar.len[j.ys];
             const int np = n - 1, mp = m - 1;
-            uint64_t bytes = 0;
-            j.stride = 1;
-            if (np >= 1 && mp >= 1) {
-                const int w = (band_override >= 0) ? window_of_band(band_override, n, m) : window_of(pct, n, m);
-                j.stride = (uint32_t)std::min(std::min(np, mp), w + 1) + 1;
-                bytes = (uint64_t)(np + mp + 1) * j.stride;
-                size_t smem = (size_t)3 * (np + 2) * sizeof(float);
-                if (smem > (size_t)smem_optin) {
-                    err = "sequence too long for the on-device trace-back kernel";
-                    return cudaSuccess;
+            if (n < 1 || m < 1 || np == 0 || mp == 0) continue;   // no DP: answered on the host below
+            const int w = (band_override >= 0) ? window_of_band(band_override, n, m) : window_of(pct, n, m);
+            j.w = w;
+            const int n_slabs = (np + PW_SLAB_ROWS - 1) / PW_SLAB_ROWS;
+            int steps_max = 1;
+            uint64_t cells = 0;
+            for (int s = 0; s < n_slabs; s++) {
+                int Jlo, Jhi;
+                pw_slab_range(s, np, mp, w, Jlo, Jhi);
+                if (Jhi >= Jlo) {
+                    steps_max = std::max(steps_max, Jhi - Jlo + 1 + 31);
+                    cells += (uint64_t)(Jhi - Jlo + 1 + 31) * 512;
                 }
-                smem_max = std::max(smem_max, smem);
             }
-            bytes = (bytes + 15) & ~15ull;
-            if (!jobs.empty() && (dir_bytes + bytes > budget || jobs.size() >= 65535)) break;
-            j.dir_off = dir_bytes;
-            dir_bytes += bytes;
+            j.steps_max = (uint32_t)steps_max;
+            const uint64_t dir_words = (uint64_t)n_slabs * steps_max * 32;
+            const uint64_t row_words = ((uint64_t)4 * ((mp + 3) >> 2) + 3) & ~3ull;
+            if (!jobs.empty() && ((words + dir_words + row_words) * 4 > budget || jobs.size() >= (1u << 24))) break;
+            j.dir_off = words;
+            words += dir_words;
+            j.row_off = words;              // multiple of 4 words: float4 accesses are aligned
+            words += row_words;
             jobs.push_back(j);
+            job_req.push_back(j.out);
+            cost.push_back(cells);
         }
+        const size_t cnt_req = (size_t)(k - done);   // requests covered by this chunk (jobs + trivial ones)
         const size_t cnt = jobs.size();
-        DevBuf d_jobs, d_dirs, d_scores, d_paths, d_lens;
-        if ((e = d_jobs.alloc(cnt * sizeof(PairJob))) != cudaSuccess) return e;
-        if ((e = d_dirs.alloc(dir_bytes)) != cudaSuccess) return e;
-        if ((e = d_scores.alloc(cnt * sizeof(float))) != cudaSuccess) return e;
-        if ((e = d_lens.alloc(cnt * sizeof(unsigned long long))) != cudaSuccess) return e;
-        if (paths_ij && (e = d_paths.alloc(cnt * path_cap * 2 * sizeof(uint32_t))) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(d_jobs.p, jobs.data(), cnt * sizeof(PairJob), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(pair_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_max, 16))) != cudaSuccess) return e;
-        pair_path_kernel<<<(unsigned)cnt, 256, std::max<size_t>(smem_max, 16), stream>>>(
-            d_arena, d_off, d_len, (const PairJob*)d_jobs.p, (int)ar.dpad, pct, band_override, ins, del, mat, strict ? 1 : 0,
-            (uint8_t*)d_dirs.p, (float*)d_scores.p, paths_ij ? (uint32_t*)d_paths.p : nullptr, path_cap,
-            (unsigned long long*)d_lens.p);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(scores + done, d_scores.p, cnt * sizeof(float), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-        std::vector<unsigned long long> lens_h(cnt);
-        if ((e = cudaMemcpyAsync(lens_h.data(), d_lens.p, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-        if (paths_ij)
-            if ((e = cudaMemcpyAsync(paths_ij + done * path_cap * 2, d_paths.p, cnt * path_cap * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
-        if (path_lens)
-            for (size_t q = 0; q < cnt; q++) path_lens[done + q] = lens_h[q];
-        done += cnt;
+        // host-answered requests (src/alignments.rs:116-125: n == m == 1 scores 0/2 = 0, a missing score cell +INF)
+        for (uint64_t q = done; q < k; q++) {
+            const int n = (int)ar.len[inv[pairs_ij[2 * q]]], m = (int)ar.len[inv[pairs_ij[2 * q + 1]]];
+            if (n < 1 || m < 1 || n - 1 == 0 || m - 1 == 0) {
+                scores[q] = (n == 1 && m == 1) ? 0.0f : INFINITY;
+                if (path_lens) path_lens[q] = 0;
+            }
+        }
+        if (cnt) {
+            std::vector<uint32_t> order(cnt);
+            std::iota(order.begin(), order.end(), 0u);
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cost[x] > cost[y]; });
+            size_t jobs_bytes = cnt * sizeof(PairJob) + cnt * sizeof(uint32_t);
+            if ((e = grow(sc.d_jobs, sc.jobs_cap, jobs_bytes)) != cudaSuccess) return e;
+            if ((e = grow(sc.d_buf, sc.cap, words * 4)) != cudaSuccess) return e;
+            if (sc.res_cap < cnt) {
+                if (sc.d_scores) cudaFree(sc.d_scores);
+                if (sc.d_lens) cudaFree(sc.d_lens);
+                sc.d_scores = nullptr; sc.d_lens = nullptr; sc.res_cap = 0;
+                if ((e = cudaMalloc((void**)&sc.d_scores, cnt * sizeof(float))) != cudaSuccess) return e;
+                if ((e = cudaMalloc((void**)&sc.d_lens, cnt * sizeof(unsigned long long))) != cudaSuccess) return e;
+                sc.res_cap = cnt;
+            }
+            if (paths_ij && (e = grow(sc.d_paths, sc.paths_cap, cnt * path_cap * 2 * sizeof(uint32_t))) != cudaSuccess) return e;
+            PairJob* d_jobs = static_cast<PairJob*>(sc.d_jobs);
+            uint32_t* d_order = reinterpret_cast<uint32_t*>(d_jobs + cnt);
+            if ((e = cudaMemcpyAsync(d_jobs, jobs.data(), cnt * sizeof(PairJob), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(d_order, order.data(), cnt * sizeof(uint32_t), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
+            if ((e = cudaMemsetAsync(sc.d_counter, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+            WaveArgs a{};
+            a.arena = d_arena; a.off = d_off; a.len = d_len;
+            a.jobs = d_jobs; a.order = d_order; a.n_jobs = (uint32_t)cnt; a.counter = sc.d_counter;
+            a.pins = ins; a.pdel = del; a.pmat = mat;
+            a.scratch = static_cast<uint32_t*>(sc.d_buf);
+            a.scores = sc.d_scores;
+            const int grid = (int)std::min<size_t>((cnt + PW_WARPS - 1) / PW_WARPS, (size_t)sm_count * 2);
+            if ((e = cudaEventRecord(sc.ev0, stream)) != cudaSuccess) return e;
+            if ((e = launch_wave_dpad(ar.dpad, a, strict, grid, stream)) != cudaSuccess) return e;
+            pair_trace_kernel<<<(unsigned)((cnt + 63) / 64), 64, 0, stream>>>(d_jobs, (uint32_t)cnt, d_len, static_cast<const uint32_t*>(sc.d_buf),
+                                                                             paths_ij ? sc.d_paths : nullptr, path_cap, sc.d_lens);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(sc.ev1, stream)) != cudaSuccess) return e;
+            std::vector<float> sc_h(cnt);
+            std::vector<unsigned long long> lens_h(cnt);
+            if ((e = cudaMemcpyAsync(sc_h.data(), sc.d_scores, cnt * sizeof(float), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(lens_h.data(), sc.d_lens, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+            // paths: jobs keep the request order, so runs of consecutive requests copy as one block
+            if (paths_ij) {
+                size_t q = 0;
+                while (q < cnt) {
+                    size_t r = q + 1;
+                    while (r < cnt && job_req[r] == job_req[r - 1] + 1) r++;
+                    if ((e = cudaMemcpyAsync(paths_ij + (done + job_req[q]) * path_cap * 2, sc.d_paths + q * path_cap * 2,
+                                             (r - q) * path_cap * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+                    q = r;
+                }
+                if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+            }
+            for (size_t q = 0; q < cnt; q++) {
+                scores[done + job_req[q]] = sc_h[q];
+                if (path_lens) path_lens[done + job_req[q]] = lens_h[q];
+            }
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, sc.ev0, sc.ev1) == cudaSuccess && ms) *ms += t;
+        }
+        done += cnt_req;
     }
     return cudaSuccess;
 }

@@ -40,8 +40,18 @@ def lib():
         L.apd_emul_cells_visited.argtypes = [C.c_uint64] * 3
         L.apd_emul_window.restype = C.c_int
         L.apd_emul_window.argtypes = [C.c_float, C.c_int, C.c_int]
+        L.apd_emul_force_rho.restype = None
+        L.apd_emul_force_rho.argtypes = [C.c_int, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
+
+
+def force_rho(rho):
+    """Row grid (0..3) for every unit, -1 = the kernel's own choice.  Returns the number of units
+    that ran on each grid since the previous call."""
+    used = np.zeros(4, dtype=np.uint64)
+    lib().apd_emul_force_rho(int(rho), used.ctypes.data_as(C.POINTER(C.c_uint64)))
+    return used
 
 
 def align_all(seqs, pct, ins=1.0, dele=1.0, mat=1.0, strict=True, rank=0, world=1):

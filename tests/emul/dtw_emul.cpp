@@ -73,6 +73,8 @@ struct HostCtx {
 };
 
 static uint64_t exact_units = 0;
+static int g_force_rho = -1;          // tests: run every unit on one fixed row grid
+static uint64_t rho_used[4] = {0, 0, 0, 0};
 static uint64_t step_counts[3] = {0, 0, 0};
 
 template <int DPAD>
@@ -86,16 +88,20 @@ int run_all(const Arena& ar, const UnitPlan& plan, float pct, Penalties pen, int
             if (u % world != rank) continue;
             const Unit un = plan.units[u];
             const int n = (int)ar.len[un.a];
-            RowGeom rg = row_geometry(n);
             LaneGeom lanes[32];
             int Jt_max = 0, wmax = 0;
+            unsigned int votes = 0;
             for (int l = 0; l < 32; l++) {
                 uint32_t b = 32 * un.B + l;
                 bool exists = b > un.a && b < N;
                 lanes[l] = lane_geometry(exists, n, exists ? (int)ar.len[b] : 0, pct);
                 if (lanes[l].Jt > Jt_max) Jt_max = lanes[l].Jt;
                 if (lanes[l].active && lanes[l].w > wmax) wmax = lanes[l].w;
+                const unsigned int v = lane_rho_votes(lanes[l], n);
+                for (int r = 0; r < 4; r++) votes += ((v >> r) & 1u) << (8 * r);
             }
+            RowGeom rg = row_geometry(n, g_force_rho >= 0 ? g_force_rho : choose_rho(votes, n));
+            rho_used[rg.rho]++;
             if (ring_tiles_needed(wmax, rg.It > 0 ? rg.It : 1) > uc.St) return -10;  // planner bug
             for (int l = 0; l < 32; l++) {
                 uint32_t b = 32 * un.B + l;
@@ -222,6 +228,15 @@ int apd_emul_plan_info(const uint32_t* lens, uint32_t n, uint32_t dim, float pct
     }
     if (pairs != (uint64_t)n * (n - 1) / 2) return -2;
     return 0;
+}
+
+// Forces the row grid (0..3) of every unit, -1 = the kernel's own choice; returns how many units
+// used each grid since the last call (4 counters).
+void apd_emul_force_rho(int rho, uint64_t* used4)
+{
+    g_force_rho = rho;
+    if (used4) for (int r = 0; r < 4; r++) used4[r] = rho_used[r];
+    for (int r = 0; r < 4; r++) rho_used[r] = 0;
 }
 
 uint64_t apd_emul_cells_visited(uint64_t n, uint64_t m, uint64_t w) { return cells_visited(n, m, w); }

@@ -151,3 +151,43 @@ def test_planner_at_full_baseline_sizes(name):
         assert want == 10000 * 9999 * 51463
     if name == "C5":
         assert int(info[8]) == 1                                                 # unbanded 4096: global ring
+
+
+@pytest.mark.parametrize("rho", [0, 1, 2, 3])
+def test_every_row_grid_gives_the_same_bits(rho):
+    """The row tiles may start at any of four offsets (dtw_core.h: row_geometry(n, rho)); the rows
+    below n-1 in the last tile are computed from the zero frames behind the sequence and must
+    never reach the score.  Every grid, hot and cold path, tie-heavy and real-valued data."""
+    rng = np.random.default_rng(500 + rho)
+    try:
+        emul.force_rho(rho)
+        for dim, pct, integer, w3 in ((2, 0.0, True, (1.0, 1.0, 1.0)), (3, 0.2, True, (0.75, 0.5, 1.0)),
+                                      (20, 0.1, False, (1.0, 1.0, 1.0)), (8, 1.0, False, (0.5, 1.0, 0.25))):
+            seqs = random_sequences(rng, 36, 1, 50, dim, integer)
+            want = oracle.align_all(seqs, pct, *w3, variant="dense")
+            for strict in (1, 2):
+                got, _ = emul.align_all(seqs, pct, *w3, strict=strict)
+                assert np.array_equal(bits(got), bits(want)), (rho, dim, pct, strict)
+        used = emul.force_rho(-1)
+        assert used[rho] > 0 and used.sum() == used[rho]
+    finally:
+        emul.force_rho(-1)
+
+
+def test_chosen_row_grid_needs_fewer_tiles_on_the_headline_shape():
+    """C3's geometry (len 512, band 10 % -> w = 53): a 4-column block needs 110 rows = 27.5 tiles.
+    The end-anchored grid (rho = 0) spends 29 tiles per block, the grid the kernel picks 28."""
+    rng = np.random.default_rng(77)
+    seqs = [rng.normal(size=(512, 4)).astype(np.float32) for _ in range(3)]
+    want = oracle.align_all(seqs, 0.1, variant="dense")
+    try:
+        emul.force_rho(0)
+        got0, info0 = emul.align_all(seqs, 0.1)
+        emul.force_rho(-1)
+        got, info = emul.align_all(seqs, 0.1)
+        used = emul.force_rho(-1)
+    finally:
+        emul.force_rho(-1)
+    assert np.array_equal(bits(got0), bits(want)) and np.array_equal(bits(got), bits(want))
+    assert used[0] == 0 and used.sum() > 0              # the anchored grid is not the one chosen here
+    assert int(info[3]) < 0.975 * int(info0[3])         # >= 2.5 % fewer lane-tiles

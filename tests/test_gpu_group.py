@@ -93,16 +93,16 @@ def test_group_without_peer_stores():
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
     code = (
-        "import numpy as np, sys\\n"
-        "sys.path.insert(0, %r)\\n"
-        "from audio_pattern_discovery_b200 import Context, synth\\n"
-        "from oracle import oracle\\n"
-        "rng = np.random.default_rng(5)\\n"
-        "seqs, _ = synth.make_sequences(90, rng.integers(30, 140, size=90), 20, 8, 31)\\n"
-        "ctx = Context(devices=[0, 1]); assert not ctx.peer_stores\\n"
-        "ctx.set_sequences(seqs); got = ctx.align_all(0.1, 1.0, 1.0, 1.0)\\n"
-        "want = oracle.align_all(seqs, 0.1, 1.0, 1.0, 1.0, workers=8, variant='dense')\\n"
-        "print('ok=%%s' %% np.array_equal(got.view(np.uint32), want.view(np.uint32)))\\n" % ROOT)
+        "import numpy as np, sys\n"
+        "sys.path.insert(0, %r)\n"
+        "from audio_pattern_discovery_b200 import Context, synth\n"
+        "from oracle import oracle\n"
+        "rng = np.random.default_rng(5)\n"
+        "seqs, _ = synth.make_sequences(90, rng.integers(30, 140, size=90), 20, 8, 31)\n"
+        "ctx = Context(devices=[0, 1]); assert not ctx.peer_stores\n"
+        "ctx.set_sequences(seqs); got = ctx.align_all(0.1, 1.0, 1.0, 1.0)\n"
+        "want = oracle.align_all(seqs, 0.1, 1.0, 1.0, 1.0, workers=8, variant='dense')\n"
+        "print('ok=%%s' %% np.array_equal(got.view(np.uint32), want.view(np.uint32)))\n" % ROOT)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, APD_NO_P2P="1"))
     assert r.returncode == 0 and "ok=True" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
