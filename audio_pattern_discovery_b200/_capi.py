@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libapd_b200.so")
+# APD_LIB_PATH selects another build of the same library (kernel experiments: build.py --variant)
+LIB_PATH = os.environ.get("APD_LIB_PATH") or os.path.join(_HERE, "libapd_b200.so")
 
 APD_OK = 0
 APD_ERR_INVALID = 1

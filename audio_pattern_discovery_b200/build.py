@@ -60,15 +60,29 @@ def _run(cmd, verbose):
         print(r.stdout + r.stderr, flush=True)
 
 
-def build(force=False, verbose=False, ptxas_info=False):
-    """Builds libapd_b200.so if sources changed; returns its path."""
+def build(force=False, verbose=False, ptxas_info=False, variant=None, defines=()):
+    """Builds libapd_b200.so if sources changed; returns its path.  `variant` (experiments only)
+    builds libapd_b200.<variant>.so with extra -D defines next to it; load it with
+    APD_LIB_PATH=<that file> (see _capi.py)."""
+    global OBJ, LIB
+    OBJ0, LIB0 = OBJ, LIB
+    try:
+        if variant:
+            OBJ = os.path.join(ROOT, "build", "obj_" + variant)
+            LIB = os.path.join(HERE, "libapd_b200.%s.so" % variant)
+        return _build(force, verbose, ptxas_info, ["-D" + d for d in defines])
+    finally:
+        OBJ, LIB = OBJ0, LIB0
+
+
+def _build(force, verbose, ptxas_info, defs):
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "fingerprint")
-    fp = _fingerprint()
+    fp = _fingerprint() + " ".join(defs)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == fp:
         return LIB
     nvcc = _nvcc()
-    extra = ["-Xptxas", "-v"] if ptxas_info else []
+    extra = (["-Xptxas", "-v"] if ptxas_info else []) + defs
     jobs = []
     objs = []
     for d in DPADS:
@@ -96,6 +110,8 @@ if __name__ == "__main__":
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--ptxas-info", action="store_true")
+    ap.add_argument("--variant", default=None, help="experiments: build libapd_b200.<variant>.so")
+    ap.add_argument("-D", dest="defines", action="append", default=[], help="extra preprocessor define for a variant build")
     a = ap.parse_args()
-    print(build(a.force, a.verbose, a.ptxas_info))
+    print(build(a.force, a.verbose, a.ptxas_info, a.variant, a.defines))
     sys.exit(0)

@@ -598,7 +598,10 @@ apd_status create_one(int device_id, apd_ctx** out)
             return APD_ERR_CUDA;                                                         \
         }                                                                                \
     } while (0)
+    PhaseTimer pt;
     APD_CREATE_CUDA(cudaSetDevice(device_id));
+    APD_CREATE_CUDA(cudaFree(0));
+    pt.lap("create: device context");
     APD_CREATE_CUDA(cudaGetDeviceProperties(&prop, device_id));
     if (prop.major < 10) {
         g_create_error = "device is not sm_100-class (compute capability " + std::to_string(prop.major) + "." +
@@ -626,6 +629,7 @@ apd_status create_one(int device_id, apd_ctx** out)
     APD_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
     APD_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_dtw, cudaEventDisableTiming));
     APD_CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    pt.lap("create: streams, events, small buffers");
 #undef APD_CREATE_CUDA
     const char* ring_env = getenv("APD_RING");
     const char* force_g = getenv("APD_FORCE_GSTATE");
@@ -671,8 +675,10 @@ void destroy_one(apd_ctx* c)
 // the caller's buffers are no longer needed (the last pieces may still be in flight).
 apd_status upload_arena(apd_ctx* c, const float* const* frames)
 {
+    PhaseTimer pt;
     apd_status s = ensure_stage_ring(c);
     if (s != APD_OK) return s;
+    pt.lap("upload: pinned ring ready");
     const Arena& ar = c->arena;
     const uint64_t frames_per_buf = std::max<uint64_t>(kStageBytes / (ar.dpad * sizeof(float)), 1);
     unsigned nt = std::thread::hardware_concurrency();
@@ -822,8 +828,10 @@ apd_status apd_group_size(apd_ctx* c, uint32_t* n_dev, uint32_t* peer_stores)
 
 apd_status apd_set_sequences(apd_ctx* c, const float* const* frames, const uint32_t* lens, uint32_t n, uint32_t dim)
 {
+    PhaseTimer pt;
     apd_status s = begin_sequences(c, lens, n, dim);
     if (s != APD_OK) return s;
+    pt.lap("set_sequences: layout + device arena");
     if (n > 0 && !frames) return fail(c, APD_ERR_INVALID, "frames is NULL");
     for (uint32_t k = 0; k < n; k++)
         if (lens[k] > 0 && !frames[k]) return fail(c, APD_ERR_INVALID, "frames[k] is NULL for a non-empty sequence");
@@ -832,6 +840,7 @@ apd_status apd_set_sequences(apd_ctx* c, const float* const* frames, const uint3
     // CPU half of the packing glue: sort + pad, piecewise through the pinned ring, overlapped with the H2D copies.
     s = upload_arena(c, frames);
     if (s != APD_OK) return s;
+    pt.lap("set_sequences: pack + H2D (pinned ring)");
     s = upload_tables(c, nullptr);
     if (s != APD_OK) return s;
     APD_CUDA(c, cudaEventRecord(c->ev_h1, c->stream));
@@ -1047,8 +1056,10 @@ apd_status apd_align_all(apd_ctx* c, const apd_params* p, float* out_nxn)
     const uint64_t N = c->arena.n;
     if (N && !out_nxn) return fail(c, APD_ERR_INVALID, "out_nxn is NULL");
     c->matrix_valid = false;
+    PhaseTimer pt;
     s = ensure_plan(c, p->warping_band_percentage);
     if (s != APD_OK) return s;
+    pt.lap("align_all: unit plan");
     const uint32_t G = (uint32_t)c->members.size();
     const bool group = G > 1;
     // A shard of a multi-process job (apd_set_shard) expands only its own units; a group gathers all of them.
@@ -1063,6 +1074,7 @@ apd_status apd_align_all(apd_ctx* c, const apd_params* p, float* out_nxn)
         s = ensure_device(m, m->d_matrix, m->matrix_cap, (size_t)(N * N));
         if (s != APD_OK) return s;
     }
+    pt.lap("align_all: result buffers");
     // DTW kernels on every member; with peer mappings they store into every member's gathered buffer.
     for (apd_ctx* m : c->members) {
         APD_CUDA(m, cudaSetDevice(m->device));
@@ -1094,6 +1106,7 @@ apd_status apd_align_all(apd_ctx* c, const apd_params* p, float* out_nxn)
         s = run_scatter(m, m->d_packed, gather_ranks, m->d_matrix, m->stream);
         if (s != APD_OK) return s;
     }
+    pt.lap("align_all: enqueue");
     // Device -> host: member g copies rows [g*N/G, (g+1)*N/G) of the matrix it assembled, so a group
     // uses G PCIe links at once (one host thread per member: the copy into pageable memory blocks).
     c->stats.d2h_bytes = N * N * sizeof(float);
@@ -1119,6 +1132,7 @@ apd_status apd_align_all(apd_ctx* c, const apd_params* p, float* out_nxn)
         for (uint32_t g = 0; g < G; g++) th.emplace_back(d2h, g);
         for (auto& x : th) x.join();
     }
+    pt.lap("align_all: kernels + D2H");
     APD_CUDA(c, cudaSetDevice(c->device));
     collect_stats(c);
     for (uint32_t g = 0; g < G; g++)

@@ -2,7 +2,12 @@
 // (design notes in pair_path.cuh).
 #include "pair_path.cuh"
 
+#include "apd_internal.h"
+
+#include <cuda_bf16.h>
+
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 
 namespace apd {
@@ -22,13 +27,38 @@ struct WaveArgs {
     float* scores;           // indexed by job
 };
 
+// Arithmetic of the local frame distance (the product ships DIST_STRICT and DIST_FAST; the
+// others exist only to MEASURE what a tensor-core formulation of the distance would do to the
+// final score, north_star (d): they emulate, on the CUDA cores, the numerics of
+// |x|^2 + |y|^2 - 2 x.y with the dot product taken from split-precision tensor-core MMAs --
+// in their most favourable form: exact products, f32 FMA accumulation).  Selected with
+// APD_EXPERIMENT_DIST=<n> for FAST-mode apd_align_pairs calls on 20-wide frames
+// (tools/tensor_core_score_error.py); never used by apd_align_all.
+enum {
+    DIST_STRICT = 0,      // the reference's operation sequence (bit-exact)
+    DIST_FAST = 1,        // difference form, FMA accumulation, approximate sqrt
+    DIST_DOT_F32 = 2,     // dot form, every product and sum in f32 FMA (the best any dot form can do)
+    DIST_DOT_3XTF32 = 3,  // dot form, x.y = xh.yh + xh.yl + xl.yh with tf32 pieces (3 MMAs, f32 accumulate)
+    DIST_DOT_1XTF32 = 4,  // dot form, single-pass tf32
+    DIST_DOT_3XTF32_CENTERED = 5,  // as 3, after subtracting the row sequence's mean frame from x and y
+    DIST_DOT_BF16X3 = 6   // dot form, 3 bf16 pieces per operand, the 6 largest cross products
+};
+
+__device__ __forceinline__ float to_tf32(float a)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(a));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float to_bf16(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
 // src/numerics.rs:114-120 for one cell.  STRICT: packed subtract and square, sequential f32
 // accumulation in dimension order, IEEE sqrt -- the same bits as K1 and the reference.  FAST:
 // the association of K1's FAST A stage (even / odd partial sums with FMAs, approximate sqrt).
-template <int DPAD, bool STRICT>
+template <int DPAD, int MODE>
 __device__ __forceinline__ float cell_distance(const F2 (&x)[DPAD / 2], const F2 (&y)[DPAD / 2])
 {
-    if (STRICT) {
+    if (MODE == DIST_STRICT) {
         float acc = 0.0f;
 #pragma unroll
         for (int k = 0; k < DPAD / 2; k++) {
@@ -39,16 +69,41 @@ __device__ __forceinline__ float cell_distance(const F2 (&x)[DPAD / 2], const F2
         }
         return sqrt_rn(acc);
     }
-    F2 acc2 = mk2(0.0f, 0.0f);
+    if (MODE == DIST_FAST) {
+        F2 acc2 = mk2(0.0f, 0.0f);
 #pragma unroll
-    for (int k = 0; k < DPAD / 2; k++) {
-        const F2 t = sub2_rn(x[k], y[k]);
-        acc2 = (k == 0) ? mul2_rn(t, t) : fma2_rn(t, t, acc2);
+        for (int k = 0; k < DPAD / 2; k++) {
+            const F2 t = sub2_rn(x[k], y[k]);
+            acc2 = (k == 0) ? mul2_rn(t, t) : fma2_rn(t, t, acc2);
+        }
+        return sqrt_fast(acc2.x + acc2.y);
     }
-    return sqrt_fast(acc2.x + acc2.y);
+    // ---- experiments: d^2 = |x|^2 + |y|^2 - 2 x.y ----
+    float nx = 0.0f, ny = 0.0f, dot = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DPAD; k++) {
+        const float a = (k & 1) ? x[k / 2].y : x[k / 2].x, b = (k & 1) ? y[k / 2].y : y[k / 2].x;
+        nx = fmaf(a, a, nx);   // the norms are per-frame constants computed once in f32 in any real kernel
+        ny = fmaf(b, b, ny);
+        if (MODE == DIST_DOT_F32) {
+            dot = fmaf(a, b, dot);
+        } else if (MODE == DIST_DOT_1XTF32) {
+            dot = fmaf(to_tf32(a), to_tf32(b), dot);
+        } else if (MODE == DIST_DOT_BF16X3) {
+            const float a1 = to_bf16(a), a2 = to_bf16(a - a1), a3 = to_bf16(a - a1 - a2);
+            const float b1 = to_bf16(b), b2 = to_bf16(b - b1), b3 = to_bf16(b - b1 - b2);
+            dot = fmaf(a1, b1, dot); dot = fmaf(a1, b2, dot); dot = fmaf(a2, b1, dot);
+            dot = fmaf(a2, b2, dot); dot = fmaf(a1, b3, dot); dot = fmaf(a3, b1, dot);
+        } else {
+            const float ah = to_tf32(a), al = to_tf32(a - ah), bh = to_tf32(b), bl = to_tf32(b - bh);
+            dot = fmaf(ah, bh, dot); dot = fmaf(ah, bl, dot); dot = fmaf(al, bh, dot);
+        }
+    }
+    const float d2 = fmaxf(fmaf(-2.0f, dot, nx + ny), 0.0f);
+    return sqrt_fast(d2);
 }
 
-template <int DPAD, bool STRICT>
+template <int DPAD, int MODE>
 __global__ void __launch_bounds__(32 * PW_WARPS) pair_wave_kernel(const WaveArgs a)
 {
     extern __shared__ float4 smem4[];
@@ -75,6 +130,31 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pair_wave_kernel(const WaveArgs
         for (int j = lane; j < 4 * Jt; j += 32) rb[j] = INF;            // row 0 of the DP: absent cells
         __syncwarp();
 
+        // experiment DIST_DOT_3XTF32_CENTERED: the row sequence's mean frame, subtracted from x and y alike
+        // (x - y is unchanged, |x|^2 and |y|^2 shrink towards the size of the differences)
+        F2 ctr[DPAD / 2];
+#pragma unroll
+        for (int v = 0; v < DPAD / 2; v++) ctr[v] = mk2(0.0f, 0.0f);
+        if (MODE == DIST_DOT_3XTF32_CENTERED) {
+            for (int t = lane; t < n; t += 32) {
+                const float4* p = xbase4 + (size_t)t * (DPAD / 4);
+#pragma unroll
+                for (int v = 0; v < DPAD / 4; v++) {
+                    const float4 f = __ldg(p + v);
+                    ctr[2 * v].x += f.x; ctr[2 * v].y += f.y; ctr[2 * v + 1].x += f.z; ctr[2 * v + 1].y += f.w;
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < DPAD / 2; v++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    ctr[v].x += __shfl_xor_sync(0xffffffffu, ctr[v].x, o);
+                    ctr[v].y += __shfl_xor_sync(0xffffffffu, ctr[v].y, o);
+                }
+                ctr[v].x /= (float)n; ctr[v].y /= (float)n;
+            }
+        }
+
         // the score cell (n', m') (src/alignments.rs:116-125)
         const int kstar = (np - 1) >> 7, lstar = ((np - 1) & 127) >> 2, rstar = (np - 1) & 3;
         const int Jstar = (mp - 1) >> 2, cstar = (mp - 1) & 3;
@@ -99,6 +179,10 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pair_wave_kernel(const WaveArgs
                     const float4 f = __ldg(p + v);
                     xr[r][2 * v] = make_float2(f.x, f.y);
                     xr[r][2 * v + 1] = make_float2(f.z, f.w);
+                    if (MODE == DIST_DOT_3XTF32_CENTERED) {
+                        xr[r][2 * v] = sub2_rn(xr[r][2 * v], ctr[2 * v]);
+                        xr[r][2 * v + 1] = sub2_rn(xr[r][2 * v + 1], ctr[2 * v + 1]);
+                    }
                 }
             }
             float left[TILE], bottom[TILE];
@@ -160,12 +244,16 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pair_wave_kernel(const WaveArgs
                             const float4 f = yt[c * (DPAD / 4) + v];
                             yv[2 * v] = make_float2(f.x, f.y);
                             yv[2 * v + 1] = make_float2(f.z, f.w);
+                            if (MODE == DIST_DOT_3XTF32_CENTERED) {
+                                yv[2 * v] = sub2_rn(yv[2 * v], ctr[2 * v]);
+                                yv[2 * v + 1] = sub2_rn(yv[2 * v + 1], ctr[2 * v + 1]);
+                            }
                         }
                         float up = top[c];
                         float dg = (c == 0) ? diag : top[c - 1];
 #pragma unroll
                         for (int r = 0; r < TILE; r++) {
-                            const float d = cell_distance<DPAD, STRICT>(xr[r], yv);
+                            const float d = cell_distance<DPAD, MODE>(xr[r], yv);
                             const float E = colprev[r];   // (i, j-1)   deletion
                             const float I = up;           // (i-1, j)   insertion
                             const float M = dg;           // (i-1, j-1) match
@@ -237,21 +325,33 @@ __global__ void __launch_bounds__(64) pair_trace_kernel(const PairJob* __restric
     path_lens[ji] = plen;
 }
 
+template <int DPAD, int MODE>
+cudaError_t launch_wave_mode(const WaveArgs& a, int grid, cudaStream_t stream)
+{
+    const size_t smem = (size_t)PW_WARPS * PW_YRING * (DPAD + 1) * sizeof(float4);
+    cudaError_t e = cudaFuncSetAttribute(pair_wave_kernel<DPAD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pair_wave_kernel<DPAD, MODE><<<grid, 32 * PW_WARPS, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
 template <int DPAD>
 cudaError_t launch_wave(const WaveArgs& a, bool strict, int grid, cudaStream_t stream)
 {
-    const size_t smem = (size_t)PW_WARPS * PW_YRING * (DPAD + 1) * sizeof(float4);
-    cudaError_t e;
-    if (strict) {
-        e = cudaFuncSetAttribute(pair_wave_kernel<DPAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        pair_wave_kernel<DPAD, true><<<grid, 32 * PW_WARPS, smem, stream>>>(a);
-    } else {
-        e = cudaFuncSetAttribute(pair_wave_kernel<DPAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        pair_wave_kernel<DPAD, false><<<grid, 32 * PW_WARPS, smem, stream>>>(a);
+    if (strict) return launch_wave_mode<DPAD, DIST_STRICT>(a, grid, stream);
+    if (DPAD == 20) {   // measurement-only distance arithmetic (see the DIST_* enum)
+        const char* ex = getenv("APD_EXPERIMENT_DIST");
+        const int mode = ex ? atoi(ex) : 0;
+        switch (mode) {
+            case DIST_DOT_F32: return launch_wave_mode<20, DIST_DOT_F32>(a, grid, stream);
+            case DIST_DOT_3XTF32: return launch_wave_mode<20, DIST_DOT_3XTF32>(a, grid, stream);
+            case DIST_DOT_1XTF32: return launch_wave_mode<20, DIST_DOT_1XTF32>(a, grid, stream);
+            case DIST_DOT_3XTF32_CENTERED: return launch_wave_mode<20, DIST_DOT_3XTF32_CENTERED>(a, grid, stream);
+            case DIST_DOT_BF16X3: return launch_wave_mode<20, DIST_DOT_BF16X3>(a, grid, stream);
+            default: break;
+        }
     }
-    return cudaGetLastError();
+    return launch_wave_mode<DPAD, DIST_FAST>(a, grid, stream);
 }
 
 cudaError_t launch_wave_dpad(uint32_t dpad, const WaveArgs& a, bool strict, int grid, cudaStream_t stream)
@@ -317,6 +417,7 @@ cudaError_t pair_paths_run(const Arena& ar, const float* d_arena, const uint32_t
     // direction scratch budget: what is free now plus what this context already holds for it
     const uint64_t budget = std::max<uint64_t>(std::min<uint64_t>((free_b + sc.cap) / 2, 64ull << 30), 64ull << 20);
 
+    PhaseTimer pt;
     uint64_t done = 0;
     while (done < n_pairs) {
         // Greedy chunk in request order: as many pairs as fit the scratch budget (at least one).
@@ -368,6 +469,7 @@ cudaError_t pair_paths_run(const Arena& ar, const float* d_arena, const uint32_t
                 if (path_lens) path_lens[q] = 0;
             }
         }
+        pt.lap("paths: job list");
         if (cnt) {
             std::vector<uint32_t> order(cnt);
             std::iota(order.begin(), order.end(), 0u);
@@ -384,6 +486,7 @@ cudaError_t pair_paths_run(const Arena& ar, const float* d_arena, const uint32_t
                 sc.res_cap = cnt;
             }
             if (paths_ij && (e = grow(sc.d_paths, sc.paths_cap, cnt * path_cap * 2 * sizeof(uint32_t))) != cudaSuccess) return e;
+            pt.lap("paths: scratch allocation");
             PairJob* d_jobs = static_cast<PairJob*>(sc.d_jobs);
             uint32_t* d_order = reinterpret_cast<uint32_t*>(d_jobs + cnt);
             if ((e = cudaMemcpyAsync(d_jobs, jobs.data(), cnt * sizeof(PairJob), cudaMemcpyHostToDevice, stream)) != cudaSuccess) return e;
@@ -407,6 +510,7 @@ cudaError_t pair_paths_run(const Arena& ar, const float* d_arena, const uint32_t
             if ((e = cudaMemcpyAsync(sc_h.data(), sc.d_scores, cnt * sizeof(float), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
             if ((e = cudaMemcpyAsync(lens_h.data(), sc.d_lens, cnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
             if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+            pt.lap("paths: kernels + scores back");
             // paths: jobs keep the request order, so runs of consecutive requests copy as one block
             if (paths_ij) {
                 size_t q = 0;
@@ -419,6 +523,7 @@ cudaError_t pair_paths_run(const Arena& ar, const float* d_arena, const uint32_t
                 }
                 if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
             }
+            pt.lap("paths: path cells back");
             for (size_t q = 0; q < cnt; q++) {
                 scores[done + job_req[q]] = sc_h[q];
                 if (path_lens) path_lens[done + job_req[q]] = lens_h[q];

@@ -18,7 +18,10 @@ namespace {
 
 __device__ __forceinline__ uint32_t order_key(float v)
 {
-    const uint32_t b = __float_as_uint(v);
+    // -0.0 and +0.0 compare equal in the reference (partial_cmp, src/numerics.rs:129): both get the
+    // key of +0.0, so a selected zero is always reported as +0.0 (a DTW matrix never holds -0.0:
+    // its entries are sums of square roots divided by a positive count)
+    const uint32_t b = (__float_as_uint(v) == 0x80000000u) ? 0u : __float_as_uint(v);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // ascending uint order == ascending float order
 }
 

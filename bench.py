@@ -482,6 +482,7 @@ def run_b200(args):
     al2.close()
     cold = {"value": cells_total / cold_total / 1e9, "unit": UNIT, "total_s": cold_total,
             "create_and_set_sequences_s": cold_create_set, "align_all_s": cold_total - cold_create_set,
+            "rank0_create_s": getattr(al2, "t_create", None), "rank0_set_sequences_s": getattr(al2, "t_set_sequences", None),
             "host_output": "pageable", "over_warm_e2e": cold_total / (e2e_ms_step / 1e3),
             "note": "fresh apd context per rank (CUDA itself already initialised in the process), unit plan built inside, "
                     "pageable destination"}

@@ -7,11 +7,15 @@
 //     let (operations, clusters) = AgglomerativeClustering::clustering(distances, n, perc);   // :196-200
 //     let grouped = AgglomerativeClustering::cluster_sets(&operations, &clusters, n);         // :203
 //
-//   learn_stage3 <sequences.bin> <Discovery.toml> <out_stem>
+//   learn_stage3 <sequences.bin> <Discovery.toml> <out_stem> [<encoder.bin>]
 //   learn_stage3 --cluster-only <matrix.apdm> <n> <perc> <out_stem>      (host only: no GPU needed)
 //
 // sequences.bin: "APDS", u32 n, u32 dim, n x u32 lengths, then the frames (f32, row-major).
-// Writes <out_stem>.apdm (n*n f32, the Vec<f32> handed to clustering) and <out_stem>.merges.txt.
+// encoder.bin (optional): "APDE", u32 n_bins, u32 n_latent, w_encode (n_bins x n_latent f32), b_encode;
+//   the sequences are then raw cepstra and `NDSequence::new(..).encoded(&nn)` (src/main.rs:150-161)
+//   runs on the device inside align_all.
+// Writes <out_stem>.apdm + .apdm.json (the Vec<f32> handed to clustering, apd_save_matrix) and
+// <out_stem>.merges.txt.
 // A failure that is a panic in the reference prints Rust's panic line and exits with 101.
 #include <cstdio>
 #include <cstring>
@@ -46,12 +50,33 @@ static std::vector<NDSequence> read_sequences(const std::string& path)
     return out;
 }
 
+static AutoEncoder read_encoder(const std::string& path)
+{
+    std::ifstream in(path, std::ios::binary);
+    if (!in) throw Panic("cannot open " + path);
+    char magic[4];
+    uint32_t n_bins = 0, n_latent = 0;
+    in.read(magic, 4);
+    in.read(reinterpret_cast<char*>(&n_bins), 4);
+    in.read(reinterpret_cast<char*>(&n_latent), 4);
+    if (!in || std::memcmp(magic, "APDE", 4) != 0) throw Panic("not an APDE file: " + path);
+    AutoEncoder nn;
+    nn.n_bins = n_bins;
+    nn.w_encode.resize((size_t)n_bins * n_latent);
+    nn.b_encode.resize(n_latent);
+    in.read(reinterpret_cast<char*>(nn.w_encode.data()), (std::streamsize)(nn.w_encode.size() * 4));
+    in.read(reinterpret_cast<char*>(nn.b_encode.data()), (std::streamsize)(nn.b_encode.size() * 4));
+    if (!in) throw Panic("truncated APDE file");
+    return nn;
+}
+
 static void write_outputs(const std::string& stem, const std::vector<float>& distances,
                           const std::vector<ClusteringOperation>& ops, const std::vector<std::vector<size_t>>& grouped)
 {
     if (!distances.empty()) {
-        std::ofstream m(stem + ".apdm", std::ios::binary);
-        m.write(reinterpret_cast<const char*>(distances.data()), (std::streamsize)(distances.size() * 4));
+        size_t n = 0;
+        while (n * n < distances.size()) n++;
+        save_matrix(stem, distances, n);
     }
     std::ofstream t(stem + ".merges.txt");
     for (const ClusteringOperation& op : ops) {
@@ -77,15 +102,16 @@ int main(int argc, char** argv)
             write_outputs(argv[5], {}, res.first, grouped);
             return 0;
         }
-        if (argc != 4) {
-            std::fprintf(stderr, "usage: %s <sequences.bin> <Discovery.toml> <out_stem>\n", argv[0]);
+        if (argc != 4 && argc != 5) {
+            std::fprintf(stderr, "usage: %s <sequences.bin> <Discovery.toml> <out_stem> [<encoder.bin>]\n", argv[0]);
             return 2;
         }
         const Discovery discover = Discovery::from_toml(argv[2]);
         std::vector<NDSequence> signals = read_sequences(argv[1]);
         std::printf("==== Starting Alignment And Clustering ==== \n");
         const size_t n = signals.size();
-        AlignmentWorkers workers(std::move(signals));
+        AlignmentWorkers workers = (argc == 5) ? AlignmentWorkers(std::move(signals), read_encoder(argv[4]))
+                                               : AlignmentWorkers(std::move(signals));
         workers.align_all(discover);
         const std::vector<float> distances = workers.result->lock().unwrap();  // .clone()
         auto res = AgglomerativeClustering::clustering(distances, n, discover.clustering_percentile);

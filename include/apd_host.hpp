@@ -124,6 +124,14 @@ struct Discovery {
     }
 };
 
+// The encoder half of src/neural.rs:13-19 (AutoEncoder): what NDSequence::encoded needs.
+// w_encode is n_bins x n_latent row-major (Mat{flat, cols}, src/numerics.rs:169-173).
+struct AutoEncoder {
+    std::vector<float> w_encode, b_encode;
+    size_t n_bins = 0;
+    size_t n_latent() const { return b_encode.size(); }  // src/neural.rs:22-24
+};
+
 namespace detail {
 
 inline void check(apd_ctx* ctx, apd_status st, const char* what)
@@ -134,22 +142,66 @@ inline void check(apd_ctx* ctx, apd_status st, const char* what)
     }
 }
 
+struct AllDevices {};
+
 struct Context {
     apd_ctx* raw = nullptr;
     explicit Context(int device = 0) { check(nullptr, apd_create(device, &raw), "apd_create"); }
+    // every visible GPU of the box in one context: the reference's single blocking align_all call
+    // (src/main.rs:189-195) fans out inside the library
+    explicit Context(AllDevices) { check(nullptr, apd_create_multi(nullptr, 0, &raw), "apd_create_multi"); }
     ~Context() { apd_destroy(raw); }
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;
-    // the spectrogram.rs glue: one pointer + length per NDSequence; the library copies and packs
-    void set_sequences(const std::vector<NDSequence>& data)
+    // The spectrogram.rs glue: one pointer + length per NDSequence; the library copies and packs.
+    // euclidean() in the reference silently assumes equal widths (src/numerics.rs:114-120 iterates
+    // x.len()); a narrower sequence would be read past its end here, so a mismatch is a Panic.
+    void set_sequences(const std::vector<const NDSequence*>& data)
     {
         std::vector<const float*> ptrs(data.size());
         std::vector<uint32_t> lens(data.size());
-        for (size_t k = 0; k < data.size(); k++) { ptrs[k] = data[k].frames.data(); lens[k] = (uint32_t)data[k].len(); }
-        const uint32_t dim = data.empty() ? 1u : (uint32_t)data[0].n_bins;
-        check(raw, apd_set_sequences(raw, ptrs.data(), lens.data(), (uint32_t)data.size(), dim), "apd_set_sequences");
+        const size_t dim = data.empty() ? 1u : data[0]->n_bins;
+        for (size_t k = 0; k < data.size(); k++) {
+            if (data[k]->n_bins != dim)
+                throw Panic("sequence " + std::to_string(k) + " has n_bins " + std::to_string(data[k]->n_bins) +
+                            " but sequence 0 has " + std::to_string(dim));
+            ptrs[k] = data[k]->frames.data();
+            lens[k] = (uint32_t)data[k]->len();
+        }
+        check(raw, apd_set_sequences(raw, ptrs.data(), lens.data(), (uint32_t)data.size(), (uint32_t)dim), "apd_set_sequences");
+    }
+    void set_sequences(const std::vector<NDSequence>& data)
+    {
+        std::vector<const NDSequence*> refs(data.size());
+        for (size_t k = 0; k < data.size(); k++) refs[k] = &data[k];
+        set_sequences(refs);
+    }
+    // `NDSequence::new(..).encoded(&nn)` of src/main.rs:150-161 on the device: the cepstra go up,
+    // AutoEncoder::predict (src/neural.rs:55-71) runs per frame on the GPU, the embeddings land in the arena.
+    void set_sequences_encoded(const std::vector<NDSequence>& cepstra, const AutoEncoder& nn)
+    {
+        std::vector<const float*> ptrs(cepstra.size());
+        std::vector<uint32_t> lens(cepstra.size());
+        for (size_t k = 0; k < cepstra.size(); k++) {
+            if (cepstra[k].n_bins != nn.n_bins) throw Panic("assertion failed: self.cols == other.rows()");  // Mat::mul, src/numerics.rs:306
+            ptrs[k] = cepstra[k].frames.data();
+            lens[k] = (uint32_t)cepstra[k].len();
+        }
+        check(raw, apd_set_sequences_encoded(raw, ptrs.data(), lens.data(), (uint32_t)cepstra.size(), (uint32_t)nn.n_bins,
+                                             nn.w_encode.data(), nn.b_encode.data(), (uint32_t)nn.n_latent()),
+              "apd_set_sequences_encoded");
     }
 };
+
+// One single-GPU context shared by every Alignment::construct_alignment call of the process
+// (creating a CUDA context per pair would cost more than the pair).
+inline Context& pair_context(std::unique_lock<std::mutex>& held)
+{
+    static std::mutex mu;
+    static Context ctx(0);
+    held = std::unique_lock<std::mutex>(mu);
+    return ctx;
+}
 
 }  // namespace detail
 
@@ -184,13 +236,21 @@ public:
     {
     }
 
+    // Cepstra in, embeddings computed on the device (row f3): `data` holds the raw cepstra and the
+    // auto-encoder is applied inside align_all instead of by NDSequence::encoded on the host.
+    AlignmentWorkers(std::vector<NDSequence> cepstra, AutoEncoder nn) : AlignmentWorkers(std::move(cepstra))
+    {
+        encoder_ = std::make_shared<AutoEncoder>(std::move(nn));
+    }
+
     // Blocking; `alignment_workers` is accepted and ignored beyond the division the reference
     // performs with it (src/alignments.rs:33 panics on 0).
     void align_all(const Discovery& params)
     {
         if (params.alignment_workers == 0) throw Panic("attempt to divide by zero");
-        detail::Context ctx(0);
-        ctx.set_sequences(*data);
+        detail::Context ctx{detail::AllDevices{}};
+        if (encoder_) ctx.set_sequences_encoded(*data, *encoder_);
+        else ctx.set_sequences(*data);
         const apd_params p{params.warping_band_percentage, params.insertion_penalty, params.deletion_penalty,
                            params.match_penalty, mode};
         auto guard = result->lock();  // locked once, not once per pair (src/alignments.rs:56)
@@ -200,7 +260,29 @@ public:
                     (unsigned long long)stats.ordered_pairs, (unsigned long long)stats.cells_reference,
                     stats.kernel_ms / 1e3, stats.kernel_ms > 0 ? stats.cells_reference / (stats.kernel_ms * 1e6) : 0.0);
     }
+
+private:
+    std::shared_ptr<AutoEncoder> encoder_;
 };
+
+// The matrix the reference keeps only in memory (src/main.rs:194-195), on disk and back
+// (<stem>.apdm + <stem>.apdm.json, see include/apd.h).
+inline void save_matrix(const std::string& stem, const std::vector<float>& distances, size_t n_instances,
+                        const std::string& params_json = "{}")
+{
+    if (distances.size() != n_instances * n_instances) throw Panic("distances must hold n_instances^2 entries");
+    detail::check(nullptr, apd_save_matrix(stem.c_str(), distances.data(), (uint32_t)n_instances, params_json.c_str()),
+                  "apd_save_matrix");
+}
+inline std::vector<float> load_matrix(const std::string& stem, size_t* n_instances)
+{
+    uint32_t n = 0;
+    detail::check(nullptr, apd_load_matrix(stem.c_str(), nullptr, 0, &n, 1), "apd_load_matrix");
+    std::vector<float> d((size_t)n * n);
+    detail::check(nullptr, apd_load_matrix(stem.c_str(), d.data(), d.size(), &n, 1), "apd_load_matrix");
+    if (n_instances) *n_instances = n;
+    return d;
+}
 
 // src/alignments.rs:99-181.  `sparse` is not materialised (the reference never reads more than
 // the score cell); the traced warping path is in `path`.
@@ -220,8 +302,9 @@ public:
     {
         n = x.len();
         m = y.len();
-        detail::Context ctx(0);
-        ctx.set_sequences(std::vector<NDSequence>{x, y});
+        std::unique_lock<std::mutex> held;
+        detail::Context& ctx = detail::pair_context(held);
+        ctx.set_sequences(std::vector<const NDSequence*>{&x, &y});
         const apd_params p{0.0f, params.insertion_penalty, params.deletion_penalty, params.match_penalty, mode};
         const uint64_t cap = n + m + 2;
         std::vector<uint32_t> cells(2 * cap);

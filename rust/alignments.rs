@@ -31,22 +31,53 @@ fn check(ctx: *mut ffi::apd_ctx, status: i32, what: &str) {
 
 struct Context(*mut ffi::apd_ctx);
 
+// The handle is only ever used by one thread at a time (behind the Mutex below).
+unsafe impl Send for Context {}
+
 impl Context {
-    fn new(device: i32) -> Context {
+    /// Every visible GPU of the box in ONE context (apd_create_multi with n_dev = 0): the
+    /// reference's one blocking `align_all` call (src/main.rs:189-195) fans out inside the library.
+    fn all_devices() -> Context {
         let mut raw: *mut ffi::apd_ctx = ptr::null_mut();
-        let st = unsafe { ffi::apd_create(device, &mut raw) };
+        let st = unsafe { ffi::apd_create_multi(ptr::null(), 0, &mut raw) };
+        check(ptr::null_mut(), st, "apd_create_multi");
+        Context(raw)
+    }
+
+    /// One GPU is plenty for single pairs.
+    fn one_device() -> Context {
+        let mut raw: *mut ffi::apd_ctx = ptr::null_mut();
+        let st = unsafe { ffi::apd_create(0, &mut raw) };
         check(ptr::null_mut(), st, "apd_create");
         Context(raw)
     }
 
     /// The spectrogram.rs glue: hands the library one pointer + length per NDSequence
-    /// (frames are row-major T x n_bins, src/spectrogram.rs:13-24, len() 152-154).
-    fn set_sequences(&self, data: &[NDSequence]) {
+    /// (frames are row-major T x n_bins, src/spectrogram.rs:13-24, len() 152-154).  The
+    /// reference's euclidean() silently assumes equal widths (src/numerics.rs:114-120 iterates
+    /// x.len()); a mismatch would read past a buffer here, so it is a panic.
+    fn set_sequences(&self, data: &[&NDSequence]) {
+        let dim = data.first().map(|s| s.n_bins).unwrap_or(1);
+        for (k, s) in data.iter().enumerate() {
+            assert!(s.n_bins == dim, "sequence {} has n_bins {} but sequence 0 has {}", k, s.n_bins, dim);
+            assert!(s.frames.len() >= s.len() * s.n_bins, "sequence {} is shorter than len() * n_bins", k);
+        }
         let ptrs: Vec<*const f32> = data.iter().map(|s| s.frames.as_ptr()).collect();
         let lens: Vec<u32> = data.iter().map(|s| s.len() as u32).collect();
-        let dim = data.first().map(|s| s.n_bins as u32).unwrap_or(1);
-        let st = unsafe { ffi::apd_set_sequences(self.0, ptrs.as_ptr(), lens.as_ptr(), data.len() as u32, dim) };
+        let st = unsafe { ffi::apd_set_sequences(self.0, ptrs.as_ptr(), lens.as_ptr(), data.len() as u32, dim as u32) };
         check(self.0, st, "apd_set_sequences");
+    }
+}
+
+/// One single-GPU context shared by every `Alignment::construct_alignment` call of the process
+/// (creating a CUDA context per pair would cost more than the pair).
+fn pair_context() -> &'static Mutex<Context> {
+    use std::sync::Once;
+    static INIT: Once = Once::new();
+    static mut CTX: Option<Mutex<Context>> = None;
+    unsafe {
+        INIT.call_once(|| CTX = Some(Mutex::new(Context::one_device())));
+        CTX.as_ref().unwrap()
     }
 }
 
@@ -73,8 +104,9 @@ impl AlignmentWorkers {
     pub fn align_all(&mut self, params: &Discovery) {
         let n = self.data.len();
         let _batch_size = (n / params.alignment_workers) + 1;
-        let ctx = Context::new(0);
-        ctx.set_sequences(&self.data);
+        let ctx = Context::all_devices();
+        let refs: Vec<&NDSequence> = self.data.iter().collect();
+        ctx.set_sequences(&refs);
         let p = ffi::apd_params {
             warping_band_percentage: params.warping_band_percentage,
             insertion_penalty: params.insertion_penalty,
@@ -146,11 +178,8 @@ impl Alignment {
     pub fn construct_alignment(&mut self, x: &NDSequence, y: &NDSequence, params: &AlignmentParams) {
         self.n = x.len();
         self.m = y.len();
-        let ctx = Context::new(0);
-        let ptrs = [x.frames.as_ptr(), y.frames.as_ptr()];
-        let lens = [self.n as u32, self.m as u32];
-        let st = unsafe { ffi::apd_set_sequences(ctx.0, ptrs.as_ptr(), lens.as_ptr(), 2, x.n_bins as u32) };
-        check(ctx.0, st, "apd_set_sequences");
+        let ctx = pair_context().lock().unwrap();
+        ctx.set_sequences(&[x, y]);
         let p = ffi::apd_params {
             warping_band_percentage: 0.0,
             insertion_penalty: params.insertion_penalty,

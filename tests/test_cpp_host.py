@@ -115,3 +115,25 @@ def test_stage3_through_the_cpp_mirror_equals_the_oracle(exe, tmp_path):
     wm, _, _ = oracle.upgma(want, 0.05)
     assert read_merges(str(tmp_path / "out.merges.txt")) == [(a, b, k, int(np.float32(dd).view(np.uint32)), t)
                                                              for a, b, k, dd, t in wm]
+
+
+@pytest.mark.gpu
+def test_stage3_with_the_encoder_on_the_device(exe, tmp_path):
+    """src/main.rs:150-161 + 187-203: cepstra in, AutoEncoder::predict on the GPU, matrix and merges out --
+    and the matrix file the C ABI wrote reads back through the Python side of the same format."""
+    from audio_pattern_discovery_b200 import matrix_io
+    rng = np.random.default_rng(6)
+    w = ((rng.random((26, 10)) - 0.5) / 10 * 6).astype(np.float32)
+    b = ((rng.random(10) - 0.5) / 10).astype(np.float32)
+    ceps = [(np.cumsum(rng.normal(size=(int(t), 26)), axis=0) * 0.4).astype(np.float32) for t in rng.integers(20, 80, size=30)]
+    write_apds(str(tmp_path / "c.bin"), ceps)
+    with open(tmp_path / "nn.bin", "wb") as f:
+        f.write(b"APDE" + struct.pack("<II", 26, 10) + w.astype("<f4").tobytes() + b.astype("<f4").tobytes())
+    (tmp_path / "Discovery.toml").write_text(TOML % ("1.0", "1.0", "1.0", "1.0", "0.05"))
+    r = subprocess.run([exe, str(tmp_path / "c.bin"), str(tmp_path / "Discovery.toml"), str(tmp_path / "out"), str(tmp_path / "nn.bin")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    emb = [oracle.ae_encode(x, w, b) for x in ceps]
+    want = oracle.align_all(emb, 1.0, 1.0, 1.0, 1.0, workers=8, variant="dense")
+    got, n, _ = matrix_io.load_matrix(str(tmp_path / "out"))       # checks the sha256 of the header too
+    assert n == 30 and np.array_equal(got.reshape(30, 30).view(np.uint32), want.view(np.uint32))

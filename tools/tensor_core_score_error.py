@@ -1,0 +1,85 @@
+"""north_star (d): would a tensor-core formulation of the local distance hold the parity bound
+ON THE FINAL SCORE?  Run on a B200:
+
+    python tools/tensor_core_score_error.py [--seqs 2000] [--pairs 20000] > profiles/r2_tensor_core_score_error.json
+
+The parity bound of BASELINE.json applies to result[i][j], a sum of ~500 local distances divided
+by (n+m), not to a single frame distance (round 1 only looked at frame distances, in numpy).
+This measures the score itself, on the GPU, on C3's own sequences: K2 (csrc/pair_path.cu)
+recomputes a random sample of ordered pairs with the distance arithmetic replaced by an
+emulation of |x|^2 + |y|^2 - 2 x.y whose dot product has the numerics of split-precision
+tensor-core MMAs in their most favourable form (exact products of the tf32 / bf16 pieces,
+f32 FMA accumulation -- a real tcgen05 accumulator is not better than that), and compares with
+the STRICT scores (bit-exact with the oracle).  The warping path may change too: that is part
+of the error a user would see.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+MODES = {1: "difference form, f32 FMA + sqrt.approx (the shipped FAST mode)",
+         2: "dot form, f32 FMA everywhere (upper bound for any dot form)",
+         3: "dot form, 3xTF32 split (xh.yh + xh.yl + xl.yh), f32 accumulate",
+         5: "dot form, 3xTF32 split, row sequence's mean frame subtracted from x and y first",
+         6: "dot form, bf16x3 split (6 cross products), f32 accumulate",
+         4: "dot form, single-pass TF32"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seqs", type=int, default=2000)
+    ap.add_argument("--pairs", type=int, default=20000)
+    a = ap.parse_args()
+    from audio_pattern_discovery_b200 import APD_MODE_FAST, APD_MODE_STRICT, Context, synth
+    c, seqs, labels = synth.make_config("C3", a.seqs)
+    rng = np.random.default_rng(606)
+    i = rng.integers(0, a.seqs, size=a.pairs)
+    j = (i + rng.integers(1, a.seqs, size=a.pairs)) % a.seqs
+    # half of the sample from the same prototype (small distances: where cancellation bites)
+    same = np.flatnonzero(labels[i] == labels[j])
+    by_label = {}
+    for k, lab in enumerate(labels):
+        by_label.setdefault(int(lab), []).append(k)
+    for q in range(0, a.pairs, 2):
+        grp = by_label[int(labels[i[q]])]
+        if len(grp) > 1:
+            cand = grp[int(rng.integers(0, len(grp)))]
+            if cand != i[q]:
+                j[q] = cand
+    pairs = np.stack([i, j], axis=1).astype(np.uint32)
+    same = labels[i] == labels[j]
+    out = {"workload": "C3 generator, %d sequences x len 512 x dim 20, band 10 %%" % a.seqs, "pairs_sampled": int(a.pairs),
+           "same_prototype_pairs": int(same.sum()), "bound": 1e-5, "full_matrix_entries": 99990000, "modes": []}
+    with Context(0) as ctx:
+        ctx.set_sequences(seqs)
+        ref = ctx.align_pairs(pairs, c["pct"], mode=APD_MODE_STRICT).astype(np.float64)
+        for mode, desc in MODES.items():
+            os.environ["APD_EXPERIMENT_DIST"] = str(mode)
+            got = ctx.align_pairs(pairs, c["pct"], mode=APD_MODE_FAST).astype(np.float64)
+            ms = ctx.stats()["path_ms"]
+            rel = np.abs(got - ref) / ref
+            edges = [0, 1e-8, 1e-7, 1e-6, 3e-6, 1e-5, 3e-5, 1e-4, 1e-3, 1e-2, np.inf]
+            hist, _ = np.histogram(rel, bins=edges)
+            rec = {"mode": mode, "arithmetic": desc, "max_rel_err": float(rel.max()), "median_rel_err": float(np.median(rel)),
+                   "p99_rel_err": float(np.quantile(rel, 0.99)), "p999_rel_err": float(np.quantile(rel, 0.999)),
+                   "fraction_over_1e-5": float((rel > 1e-5).mean()),
+                   "expected_entries_over_1e-5_in_full_C3": float((rel > 1e-5).mean() * 99990000),
+                   "max_rel_err_same_prototype": float(rel[same].max()) if same.any() else None,
+                   "max_rel_err_other": float(rel[~same].max()) if (~same).any() else None,
+                   "histogram_edges": [float(e) if np.isfinite(e) else "inf" for e in edges], "histogram_counts": hist.tolist(),
+                   "kernel_ms_sample": ms, "holds_1e-5": bool(rel.max() <= 1e-5)}
+            out["modes"].append(rec)
+            print("mode %d: max %.3e  p99.9 %.3e  over-1e-5 %.4f%%  (%s)" % (mode, rec["max_rel_err"], rec["p999_rel_err"],
+                                                                           100 * rec["fraction_over_1e-5"], desc), file=sys.stderr)
+        os.environ.pop("APD_EXPERIMENT_DIST", None)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
