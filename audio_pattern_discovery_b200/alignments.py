@@ -305,6 +305,20 @@ class AlignmentWorkers:
     def new(data, device=None, mode=APD_MODE_STRICT, devices=None):
         return AlignmentWorkers(data, device, mode, devices)
 
+    @staticmethod
+    def new_encoded(cepstra, w_encode, b_encode, device=None, mode=APD_MODE_STRICT, devices=None):
+        """`NDSequence::new(..).encoded(&nn)` of src/main.rs:150-161 moved onto the device: `cepstra` are the
+        raw (T, n_bins) sequences, the auto-encoder (src/neural.rs:55-71) runs on the GPU and the embeddings
+        go straight into the arena.  `data` keeps the cepstra."""
+        w = AlignmentWorkers.__new__(AlignmentWorkers)
+        w.data = list(cepstra)
+        n = len(w.data)
+        w.result = _Mutex(np.zeros(n * n, dtype=np.float32))
+        w.mode = mode
+        w._ctx = Context(device) if device is not None else Context(devices="all" if devices is None else devices)
+        w._ctx.set_sequences_encoded(w.data, w_encode, b_encode)
+        return w
+
     def align_all(self, params):
         """params: a Discovery (src/discovery.rs:7-26).  Blocking; fills self.result."""
         n = len(self.data)

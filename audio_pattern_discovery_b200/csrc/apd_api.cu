@@ -53,7 +53,8 @@ struct DevStatus {            // device-side flags of one align call, read back 
 };
 
 enum { STAGE_BUFS = 3, MAX_CLASSES = SMEM_RING_CAPS + 1 };
-const size_t kStageBytes = 16u << 20;  // one buffer of the pinned upload ring
+const size_t kStageBytesMax = 16u << 20;  // one buffer of the pinned upload ring (small uploads get smaller buffers:
+                                          // pinning costs ~0.7 ms per MB, which a cold first call of a small job would notice)
 
 }  // namespace
 
@@ -115,10 +116,12 @@ struct apd_ctx {
     bool matrix_valid = false;               // d_matrix (of the leader) holds the last apd_align_all result
     float* h_stage[STAGE_BUFS] = {nullptr, nullptr, nullptr};   // pinned upload ring
     void* h_stage_raw[STAGE_BUFS] = {nullptr, nullptr, nullptr};
+    size_t stage_bytes = 0;                  // size of each ring buffer
     cudaEvent_t ev_stage[STAGE_BUFS] = {nullptr, nullptr, nullptr};
     int ring_floor = RING_TMEM;              // APD_RING / APD_FORCE_GSTATE, read once at creation
     bool debug = false;                      // APD_DEBUG
     bool concurrent_classes = true;          // APD_SERIAL_CLASSES=1 turns it off
+    bool wide = false;                       // APD_WIDE: the 12-warps-per-SM kernel where the ring fits tensor memory
 
     apd_stats stats{};
     std::string err;
@@ -432,7 +435,11 @@ apd_status run_dtw(apd_ctx* m, const apd_params* p, float* const* outs, uint32_t
         k_range(uc.begin, uc.end, m->rank, m->world, q.k0, q.k1);
         if (q.k1 <= q.k0) continue;
         q.ring = RING_GLOBAL;
-        if (ring_floor == RING_TMEM && uc.St <= TMEM_RING_TILES) q.ring = RING_TMEM;
+        // (a ring up to TMEM_SPILL_TILES taller than tensor memory holds spills its tail to shared memory
+        // and still runs 2 CTAs x 4 warps per SM)
+        if (ring_floor == RING_TMEM && uc.St <= TMEM_RING_TILES + TMEM_SPILL_TILES) q.ring = RING_TMEM;
+        // 12 warps per SM on 4 x 2-column tiles where the ring fits tensor memory outright
+        if (q.ring == RING_TMEM && L->wide && uc.St <= TMEM_RING_TILES) q.ring = RING_WIDE;
         else if (ring_floor != RING_GLOBAL && !uc.gstate) q.ring = RING_SMEM;
         q.smem = dtw_smem_bytes((int)ar.dpad, uc.St, q.ring);
         if (q.smem > m->smem_optin) return fail(m, APD_ERR_INTERNAL, "ring does not fit in shared memory");
@@ -475,7 +482,7 @@ apd_status run_dtw(apd_ctx* m, const apd_params* p, float* const* outs, uint32_t
             char line[256];
             snprintf(line, sizeof(line), "%s{\"ring\": \"%s\", \"ring_tiles\": %d, \"units\": %llu, \"ctas\": %d, \"warps_per_cta\": %d, "
                      "\"ctas_per_sm\": %d, \"smem_bytes\": %zu}", m->launch_desc.empty() ? "" : ", ",
-                     q.ring == RING_TMEM ? "tmem" : (q.ring == RING_SMEM ? "smem" : "global"), uc.St,
+                     q.ring == RING_WIDE ? "tmem+smem, 12 warps" : (q.ring == RING_TMEM ? (uc.St > TMEM_RING_TILES ? "tmem+smem" : "tmem") : (q.ring == RING_SMEM ? "smem" : "global")), uc.St,
                      (unsigned long long)(q.k1 - q.k0), q.grid, dtw_cta_warps(q.ring), q.occ, q.smem);
             m->launch_desc += line;
             if (L->debug) fprintf(stderr, "[apd] dev %d class %zu: %s\n", m->device, ci, line);
@@ -564,21 +571,40 @@ void set_sequence_stats(apd_ctx* c, uint32_t n, uint64_t h2d_bytes)
     c->stats.ordered_pairs = (uint64_t)n * (n ? n - 1 : 0);
 }
 
-apd_status ensure_stage_ring(apd_ctx* c)
+void release_stage_ring(apd_ctx* c)
 {
-    if (c->h_stage[0]) return APD_OK;
+    for (int b = 0; b < STAGE_BUFS; b++) {
+        if (c->h_stage_raw[b]) { cudaHostUnregister(c->h_stage_raw[b]); free(c->h_stage_raw[b]); }
+        c->h_stage_raw[b] = nullptr;
+        c->h_stage[b] = nullptr;
+    }
+    c->stage_bytes = 0;
+}
+
+// The pinned ring the uploads are staged through: STAGE_BUFS buffers of about a third of the
+// upload each (1 MB .. 16 MB), grown when a later upload is bigger.
+apd_status ensure_stage_ring(apd_ctx* c, size_t upload_bytes)
+{
+    size_t want = (upload_bytes / STAGE_BUFS + (1u << 20)) & ~((size_t)(1u << 20) - 1);
+    want = std::min(std::max<size_t>(want, 1u << 20), kStageBytesMax);
+    if (c->h_stage[0] && c->stage_bytes >= want) return APD_OK;
+    if (c->h_stage[0]) {
+        for (int b = 0; b < STAGE_BUFS; b++) APD_CUDA(c, cudaEventSynchronize(c->ev_stage[b]));
+        release_stage_ring(c);
+    }
     for (int b = 0; b < STAGE_BUFS; b++) {
         // page-aligned host memory, registered (pinned) in place: several times cheaper than
         // cudaMallocHost, which matters for the first call of a fresh context
         void* raw = nullptr;
-        if (posix_memalign(&raw, 4096, kStageBytes) != 0) return fail(c, APD_ERR_INTERNAL, "out of host memory");
-        std::memset(raw, 0, kStageBytes);
-        cudaError_t e = cudaHostRegister(raw, kStageBytes, cudaHostRegisterPortable);
+        if (posix_memalign(&raw, 4096, want) != 0) return fail(c, APD_ERR_INTERNAL, "out of host memory");
+        std::memset(raw, 0, want);
+        cudaError_t e = cudaHostRegister(raw, want, cudaHostRegisterPortable);
         if (e != cudaSuccess) { free(raw); return fail(c, APD_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
         c->h_stage_raw[b] = raw;
         c->h_stage[b] = static_cast<float*>(raw);
-        APD_CUDA(c, cudaEventCreateWithFlags(&c->ev_stage[b], cudaEventDisableTiming));
+        if (!c->ev_stage[b]) APD_CUDA(c, cudaEventCreateWithFlags(&c->ev_stage[b], cudaEventDisableTiming));
     }
+    c->stage_bytes = want;
     return APD_OK;
 }
 
@@ -638,6 +664,8 @@ apd_status create_one(int device_id, apd_ctx** out)
     c->debug = getenv("APD_DEBUG") != nullptr;
     const char* ser = getenv("APD_SERIAL_CLASSES");
     c->concurrent_classes = !(ser && ser[0] == '1');
+    const char* wide = getenv("APD_WIDE");
+    c->wide = wide ? (wide[0] == '1') : false;
     c->stats.sm_clock_mhz = c->sm_clock_mhz;
     c->stats.sm_count = (uint32_t)c->sm_count;
     c->members.push_back(c);
@@ -659,10 +687,9 @@ void destroy_one(apd_ctx* c)
     for (void* p : dptrs) if (p) cudaFree(p);
     c->path_scratch.release();
     if (c->h_status) cudaFreeHost(c->h_status);
-    for (int b = 0; b < STAGE_BUFS; b++) {
-        if (c->h_stage_raw[b]) { cudaHostUnregister(c->h_stage_raw[b]); free(c->h_stage_raw[b]); }
+    release_stage_ring(c);
+    for (int b = 0; b < STAGE_BUFS; b++)
         if (c->ev_stage[b]) cudaEventDestroy(c->ev_stage[b]);
-    }
     cudaEvent_t evs[] = {c->ev_k0, c->ev_k1, c->ev_s0, c->ev_s1, c->ev_h0, c->ev_h1, c->ev_d0, c->ev_d1,
                          c->ev_done, c->ev_dtw, c->ev_fork};
     for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
@@ -676,11 +703,11 @@ void destroy_one(apd_ctx* c)
 apd_status upload_arena(apd_ctx* c, const float* const* frames)
 {
     PhaseTimer pt;
-    apd_status s = ensure_stage_ring(c);
+    const Arena& ar = c->arena;
+    apd_status s = ensure_stage_ring(c, (size_t)ar.total_frames * ar.dpad * sizeof(float));
     if (s != APD_OK) return s;
     pt.lap("upload: pinned ring ready");
-    const Arena& ar = c->arena;
-    const uint64_t frames_per_buf = std::max<uint64_t>(kStageBytes / (ar.dpad * sizeof(float)), 1);
+    const uint64_t frames_per_buf = std::max<uint64_t>(c->stage_bytes / (ar.dpad * sizeof(float)), 1);
     unsigned nt = std::thread::hardware_concurrency();
     nt = std::max(1u, std::min(nt, 8u));
     int b = 0;
@@ -911,7 +938,7 @@ apd_status apd_set_sequences_encoded(apd_ctx* c, const float* const* cepstra, co
     const size_t wfloats = (size_t)n_bins * n_latent + n_latent;
     s = ensure_device(c, c->d_aux, c->aux_cap, wfloats);
     if (s != APD_OK) return s;
-    s = ensure_stage_ring(c);
+    s = ensure_stage_ring(c, (size_t)extent * sizeof(float));
     if (s != APD_OK) return s;
     APD_CUDA(c, cudaEventRecord(c->ev_h0, c->stream));
     // weights: one small pageable copy each (staged before the call returns)
@@ -919,7 +946,7 @@ apd_status apd_set_sequences_encoded(apd_ctx* c, const float* const* cepstra, co
     APD_CUDA(c, cudaMemcpyAsync(c->d_aux + (size_t)n_bins * n_latent, b_encode, n_latent * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     // cepstra through the pinned ring, sequence by sequence in sorted order
     {
-        const uint64_t buf_floats = kStageBytes / sizeof(float);
+        const uint64_t buf_floats = c->stage_bytes / sizeof(float);
         int b = 0;
         uint64_t chunk = 0, fill = 0, dst0 = 0;
         auto flush = [&]() -> apd_status {

@@ -15,6 +15,13 @@ namespace apd {
 template <bool STRICT, bool UNITW, int RING>
 static cudaError_t launch_one(const KernelArgs& a, int grid, size_t smem, cudaStream_t stream)
 {
+    if (RING == RING_WIDE) {
+        auto kern = dtw_units_wide_kernel<APD_DPAD, STRICT, UNITW>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, 32 * WIDE_WARPS, smem, stream>>>(a);
+        return cudaGetLastError();
+    }
     if (RING == RING_TMEM) {
         auto kern = dtw_units_tmem_kernel<APD_DPAD, STRICT, UNITW>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -22,7 +29,7 @@ static cudaError_t launch_one(const KernelArgs& a, int grid, size_t smem, cudaSt
         kern<<<grid, 32 * TMEM_WARPS, smem, stream>>>(a);
         return cudaGetLastError();
     }
-    auto kern = dtw_units_kernel<APD_DPAD, STRICT, UNITW, RING == RING_TMEM ? RING_SMEM : RING>;
+    auto kern = dtw_units_kernel<APD_DPAD, STRICT, UNITW, (RING == RING_TMEM || RING == RING_WIDE) ? RING_SMEM : RING>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, 32, smem, stream>>>(a);
@@ -32,6 +39,14 @@ static cudaError_t launch_one(const KernelArgs& a, int grid, size_t smem, cudaSt
 template <bool STRICT, bool UNITW, int RING>
 static cudaError_t occupancy_one(size_t smem, int* blocks_per_sm)
 {
+    if (RING == RING_WIDE) {
+        // one CTA per SM by construction (it allocates all 512 tensor-memory columns)
+        auto kern = dtw_units_wide_kernel<APD_DPAD, STRICT, UNITW>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        *blocks_per_sm = 1;
+        return cudaSuccess;
+    }
     if (RING == RING_TMEM) {
         auto kern = dtw_units_tmem_kernel<APD_DPAD, STRICT, UNITW>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -46,10 +61,16 @@ static cudaError_t occupancy_one(size_t smem, int* blocks_per_sm)
         int by_regs = regs_per_cta > 0 ? 65536 / regs_per_cta : 1;
         int occ = 512 / TMEM_COLS;
         if (by_regs < occ) occ = by_regs;
+        int dev = 0, smem_sm = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess) {
+            const int by_smem = (int)(smem_sm / (smem + 1024));   // 1 KB per resident CTA is reserved by the system
+            if (by_smem < occ) occ = by_smem;
+        }
         *blocks_per_sm = occ < 1 ? 1 : occ;
         return cudaSuccess;
     }
-    auto kern = dtw_units_kernel<APD_DPAD, STRICT, UNITW, RING == RING_TMEM ? RING_SMEM : RING>;
+    auto kern = dtw_units_kernel<APD_DPAD, STRICT, UNITW, (RING == RING_TMEM || RING == RING_WIDE) ? RING_SMEM : RING>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kern, 32, smem);
@@ -57,6 +78,7 @@ static cudaError_t occupancy_one(size_t smem, int* blocks_per_sm)
 
 #define APD_DISPATCH_RING(FN, S, U, ...)                                          \
     do {                                                                          \
+        if (ring == RING_WIDE) return FN<S, U, RING_WIDE>(__VA_ARGS__);           \
         if (ring == RING_TMEM) return FN<S, U, RING_TMEM>(__VA_ARGS__);           \
         if (ring == RING_GLOBAL) return FN<S, U, RING_GLOBAL>(__VA_ARGS__);       \
         return FN<S, U, RING_SMEM>(__VA_ARGS__);                                  \

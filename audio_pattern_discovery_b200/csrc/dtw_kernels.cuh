@@ -20,6 +20,11 @@
 //                tcgen05.st / tcgen05.ld (.32x32b.x8).  TMEM is otherwise idle here (no
 //                MMA), it costs no shared memory and no L2 traffic, and leaves occupancy to
 //                the register file: CTAs of 4 warps, 256 columns each, 2 CTAs per SM.
+//                Rings a little taller than the 32 tiles that fit (up to TMEM_RING_TILES +
+//                TMEM_SPILL_TILES) keep their first 32 slots in tensor memory and the rest in
+//                shared memory (same layout as RING_SMEM), which still leaves room for 2 CTAs
+//                of 4 warps per SM -- 8 resident warps instead of the 3-4 of a pure
+//                shared-memory ring.
 //   RING_SMEM    in shared memory (layout above), single-warp CTAs; bands too tall for
 //                256 TMEM columns.
 //   RING_GLOBAL  in a per-warp slice of a global scratch buffer (same layout, coalesced
@@ -68,10 +73,11 @@ struct KernelArgs {
 #if defined(__CUDACC__)
 
 enum { X_BAR_F4 = 2 };  // float4 slots holding the X_STAGES mbarriers behind the stage buffers
-enum { RING_SMEM = 0, RING_GLOBAL = 1, RING_TMEM = 2 };
+enum { RING_SMEM = 0, RING_GLOBAL = 1, RING_TMEM = 2, RING_WIDE = 3 };
 enum { TMEM_WARPS = 4, TMEM_COLS = 256, TMEM_RING_TILES = TMEM_COLS / 8 };
+enum { TMEM_SPILL_TILES = 25 };  // slots of a RING_TMEM ring that may live in shared memory: 2 CTAs x 4 warps x 25 KB < 227 KB
 
-template <int DPAD, int RING>
+template <int DPAD, int RING, int TC = TILE>
 struct DevCtx {
     LaneGeom lg;
     RowGeom rg;
@@ -86,6 +92,7 @@ struct DevCtx {
     float4* ring4;         // this lane's ring column: tile s, half h at ring4[(2 * s + h) * 32]
     int St;                // ring size in tiles
     uint32_t taddr;        // RING_TMEM: (first lane of the warp's quadrant << 16) | first column
+    int tcap;              // RING_TMEM: ring slots held in tensor memory (the rest, if any, in shared memory)
     unsigned int tiles;
 
     APD_D void sweep_info(int J, int& Ilo, int& Ihi, int& Nlo, int& Nhi) const
@@ -197,7 +204,7 @@ struct DevCtx {
     APD_D const float* x_tile(int buf) const { return reinterpret_cast<const float*>(xs4 + buf * DPAD); }
     APD_D void ring_load(int slot, F2 (&v)[TILE]) const
     {
-        if (RING == RING_TMEM) {
+        if (RING == RING_TMEM && slot < tcap) {
             // Outputs go straight into v's registers: nothing may read them before ring_wait().
             asm volatile(
                 "tcgen05.wait::st.sync.aligned;\n"
@@ -206,6 +213,7 @@ struct DevCtx {
                   "=f"(v[3].y)
                 : "r"(taddr + 8u * (uint32_t)slot));
         } else {
+            if (RING == RING_TMEM) slot -= tcap;   // the ring's tail in shared memory
             const float4 a = ring4[(2 * slot) * 32], b = ring4[(2 * slot + 1) * 32];
             v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w);
             v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
@@ -234,7 +242,7 @@ struct DevCtx {
     // Completion of the store is awaited by the next ring_load (tcgen05.wait::st there).
     APD_D void ring_store(int slot, const F2 (&v)[TILE])
     {
-        if (RING == RING_TMEM) {
+        if (RING == RING_TMEM && slot < tcap) {
             asm volatile(
                 "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
                 :
@@ -242,6 +250,7 @@ struct DevCtx {
                   "r"(__float_as_uint(v[1].x)), "r"(__float_as_uint(v[1].y)), "r"(__float_as_uint(v[2].x)),
                   "r"(__float_as_uint(v[2].y)), "r"(__float_as_uint(v[3].x)), "r"(__float_as_uint(v[3].y)));
         } else {
+            if (RING == RING_TMEM) slot -= tcap;
             ring4[(2 * slot) * 32] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
             ring4[(2 * slot + 1) * 32] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
         }
@@ -249,7 +258,7 @@ struct DevCtx {
     }
     APD_D F2 ring_load_last(int slot) const
     {
-        if (RING == RING_TMEM) {
+        if (RING == RING_TMEM && slot < tcap) {
             uint32_t r0, r1;
             asm volatile(
                 "tcgen05.wait::st.sync.aligned;\n"
@@ -259,19 +268,20 @@ struct DevCtx {
                 : "r"(taddr + 8u * (uint32_t)slot + 6u));
             return make_float2(__uint_as_float(r0), __uint_as_float(r1));
         }
+        if (RING == RING_TMEM) slot -= tcap;
         const float2* p = reinterpret_cast<const float2*>(ring4 + (2 * slot + 1) * 32);
         return p[1];
     }
     APD_D const float4* yaddr(int J) const
     {
-        return ybase4 + (ptrdiff_t)(4 * J - lg.gamma - 1) * (DPAD / 4);
+        return ybase4 + (ptrdiff_t)(TC * J - lg.gamma - 1) * (DPAD / 4);
     }
-    APD_D void switch_y(int J, F2 (&yv)[TILE][DPAD / 2]) const
+    APD_D void switch_y(int J, F2 (&yv)[TC][DPAD / 2]) const
     {
         if (J < lg.Jt) {
             const float4* p = yaddr(J);
 #pragma unroll
-            for (int c = 0; c < TILE; c++)
+            for (int c = 0; c < TC; c++)
 #pragma unroll
                 for (int q = 0; q < DPAD / 4; q++) {
                     float4 v = __ldg(p + c * (DPAD / 4) + q);
@@ -282,15 +292,15 @@ struct DevCtx {
         if (J + 1 < lg.Jt) {  // the next block's frames: pull them towards the SM
             const char* p = reinterpret_cast<const char*>(yaddr(J + 1));
 #pragma unroll
-            for (int o = 0; o < TILE * DPAD * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + TILE * DPAD * 4 - 4));
+            for (int o = 0; o < TC * DPAD * 4; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p + TC * DPAD * 4 - 4));
         }
     }
 };
 
 // The persistent work loop of one warp: pulls 32-pair units from the class counter.
-template <int DPAD, bool STRICT, bool UNITW, int RING>
-APD_D void warp_unit_loop(const KernelArgs& a, DevCtx<DPAD, RING>& ctx)
+template <int DPAD, bool STRICT, bool UNITW, int RING, int TC>
+APD_D void warp_unit_loop(const KernelArgs& a, DevCtx<DPAD, RING, TC>& ctx)
 {
     const int lane = ctx.lane;
     const float4* arena4 = reinterpret_cast<const float4*>(a.arena);
@@ -305,7 +315,7 @@ APD_D void warp_unit_loop(const KernelArgs& a, DevCtx<DPAD, RING>& ctx)
         const bool exists = (b > un.a) && (b < a.N);
         const int n = (int)a.len[un.a];
         const int m = exists ? (int)a.len[b] : 0;
-        ctx.lg = lane_geometry(exists, n, m, a.pct);
+        ctx.lg = lane_geometry(exists, n, m, a.pct, TC);
         {   // the row grid that costs the fewest tiles for most of the warp's lanes (dtw_core.h: choose_rho)
             const unsigned int v = lane_rho_votes(ctx.lg, n);
             unsigned int votes = 0;
@@ -316,7 +326,7 @@ APD_D void warp_unit_loop(const KernelArgs& a, DevCtx<DPAD, RING>& ctx)
         const int Jt_max = __reduce_max_sync(0xffffffffu, ctx.lg.Jt);
         const int wmax = __reduce_max_sync(0xffffffffu, ctx.lg.active ? ctx.lg.w : 0);
         float s1 = APD_INF, s2 = APD_INF;  // an empty side scores +INF (src/alignments.rs:116-125)
-        if (ring_tiles_needed(wmax, ctx.rg.It > 0 ? ctx.rg.It : 1) > a.St) {
+        if (ring_tiles_needed(wmax, ctx.rg.It > 0 ? ctx.rg.It : 1, TC) > a.St) {
             if (lane == 0) atomicExch(a.error_flag, 1);
             s1 = s2 = __int_as_float(0x7fc00000);
         } else if (Jt_max > 0) {
@@ -324,10 +334,10 @@ APD_D void warp_unit_loop(const KernelArgs& a, DevCtx<DPAD, RING>& ctx)
             ctx.ybase4 = arena4 + (size_t)(exists ? a.off[b] : a.off[un.a]) * (DPAD / 4);
             SqrtFlags fl;
             flags_reset(fl);
-            F2 acc = run_unit<DPAD, STRICT, UNITW>(ctx, ctx.lg, ctx.rg, Jt_max, a.St, a.pen, fl);
+            F2 acc = run_unit<DPAD, TC, STRICT, UNITW>(ctx, ctx.lg, ctx.rg, Jt_max, a.St, a.pen, fl);
             if (STRICT && __any_sync(0xffffffffu, ctx.lg.active && flags_bad(fl))) {
                 __syncwarp();
-                acc = run_unit_exact<DPAD, UNITW>(ctx, ctx.lg, ctx.rg, Jt_max, a.St, a.pen);
+                acc = run_unit_exact<DPAD, TC, UNITW>(ctx, ctx.lg, ctx.rg, Jt_max, a.St, a.pen);
             }
             if (ctx.lg.active) {
                 s1 = finish_score(acc.x, n, m);
@@ -360,10 +370,11 @@ __global__ void __launch_bounds__(32) dtw_units_kernel(const KernelArgs a)
                                          : smem4 + X_STAGES * DPAD + X_BAR_F4;
     ctx.ring4 = ring + lane;
     ctx.taddr = 0;
+    ctx.tcap = 0;
     ctx.St = a.St;
     ctx.tiles = 0;
     ctx.x_init();
-    warp_unit_loop<DPAD, STRICT, UNITW, RING>(a, ctx);
+    warp_unit_loop<DPAD, STRICT, UNITW, RING, TILE>(a, ctx);
 }
 
 // RING_TMEM: CTAs of TMEM_WARPS independent warps sharing one tensor-memory allocation of
@@ -387,20 +398,76 @@ __global__ void __launch_bounds__(32 * TMEM_WARPS, 2) dtw_units_tmem_kernel(cons
 
     DevCtx<DPAD, RING_TMEM> ctx;
     ctx.lane = lane;
-    ctx.xs4 = smem4 + warp * (X_STAGES * DPAD + X_BAR_F4);
+    const int spill = a.St > TMEM_RING_TILES ? a.St - TMEM_RING_TILES : 0;   // ring slots kept in shared memory
+    float4* wbase = smem4 + warp * (X_STAGES * DPAD + X_BAR_F4 + spill * 2 * 32);
+    ctx.xs4 = wbase;
     ctx.xs_smem = (uint32_t)__cvta_generic_to_shared(ctx.xs4);
     ctx.bar_smem = ctx.xs_smem + X_STAGES * DPAD * 16;
-    ctx.ring4 = nullptr;
+    ctx.ring4 = wbase + X_STAGES * DPAD + X_BAR_F4 + lane;
     ctx.taddr = tmem_base + ((uint32_t)(32 * warp) << 16);
+    ctx.tcap = TMEM_RING_TILES;
     ctx.St = a.St;
     ctx.tiles = 0;
     ctx.x_init();
-    warp_unit_loop<DPAD, STRICT, UNITW, RING_TMEM>(a, ctx);
+    warp_unit_loop<DPAD, STRICT, UNITW, RING_TMEM, TILE>(a, ctx);
 
     asm volatile("tcgen05.fence::before_thread_sync;\n");
     __syncthreads();
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS));
+    }
+}
+
+// RING_WIDE: ONE CTA of WIDE_WARPS = 12 independent warps per SM (3 per scheduler instead of 2)
+// running the 4 x 2-column tile program.  Two columns of y cost 40 registers instead of 80, so the
+// lane program fits the 168 registers a scheduler's register file allows three warps, and the
+// third warp fills the issue slots the other two leave while they wait on each other's FMA-pipe
+// work.  The CTA owns all 512 tensor-memory columns: warps 0..7 keep their boundary ring there
+// (quadrant = warp & 3, column half = warp >> 2: 256 columns = 32 tiles each), warps 8..11 keep
+// theirs in shared memory (same layout as RING_SMEM).  Rings taller than 32 tiles stay with the
+// 8-warp kernels above.
+enum { WIDE_WARPS = 12, WIDE_TMEM_WARPS = 8, WIDE_TC = 2 };
+
+template <int DPAD, bool STRICT, bool UNITW>
+__global__ void __launch_bounds__(32 * WIDE_WARPS, 1) dtw_units_wide_kernel(const KernelArgs a)
+{
+    extern __shared__ float4 smem4[];
+    __shared__ uint32_t tmem_base_smem;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_smem);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+    const uint32_t tmem_base = tmem_base_smem;
+
+    DevCtx<DPAD, RING_TMEM, WIDE_TC> ctx;
+    ctx.lane = lane;
+    constexpr int XW = X_STAGES * DPAD + X_BAR_F4;   // float4 per warp: x stage + barriers
+    ctx.xs4 = smem4 + warp * XW;
+    ctx.xs_smem = (uint32_t)__cvta_generic_to_shared(ctx.xs4);
+    ctx.bar_smem = ctx.xs_smem + X_STAGES * DPAD * 16;
+    if (warp < WIDE_TMEM_WARPS) {
+        ctx.taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * TMEM_COLS);
+        ctx.tcap = TMEM_RING_TILES;
+        ctx.ring4 = nullptr;
+    } else {
+        ctx.taddr = 0;
+        ctx.tcap = 0;   // every slot in shared memory
+        ctx.ring4 = smem4 + WIDE_WARPS * XW + (size_t)(warp - WIDE_TMEM_WARPS) * ((size_t)a.St * 2 * 32) + lane;
+    }
+    ctx.St = a.St;
+    ctx.tiles = 0;
+    ctx.x_init();
+    warp_unit_loop<DPAD, STRICT, UNITW, RING_TMEM, WIDE_TC>(a, ctx);
+
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u));
     }
 }
 
@@ -430,9 +497,13 @@ APD_DECLARE_DPAD(32)
 inline size_t dtw_smem_bytes(int dpad, int St, int ring)
 {
     size_t x = (size_t)X_STAGES * 4 * dpad * sizeof(float) + X_BAR_F4 * 16;
-    if (ring == RING_TMEM) return x * TMEM_WARPS;
+    if (ring == RING_WIDE) return x * 12 + (size_t)4 * St * TILE * 32 * sizeof(float2);   // WIDE_WARPS, 4 shared-memory rings
+    if (ring == RING_TMEM) {
+        const int spill = St > TMEM_RING_TILES ? St - TMEM_RING_TILES : 0;
+        return (x + (size_t)spill * TILE * 32 * sizeof(float2)) * TMEM_WARPS;
+    }
     return ring == RING_GLOBAL ? x : x + (size_t)St * TILE * 32 * sizeof(float2);
 }
-inline int dtw_cta_warps(int ring) { return ring == RING_TMEM ? TMEM_WARPS : 1; }
+inline int dtw_cta_warps(int ring) { return ring == RING_WIDE ? 12 : (ring == RING_TMEM ? 4 : 1); }
 
 }  // namespace apd

@@ -415,7 +415,8 @@ cudaError_t pair_paths_run(const Arena& ar, const float* d_arena, const uint32_t
     size_t free_b = 0, total_b = 0;
     if ((e = cudaMemGetInfo(&free_b, &total_b)) != cudaSuccess) return e;
     // direction scratch budget: what is free now plus what this context already holds for it
-    const uint64_t budget = std::max<uint64_t>(std::min<uint64_t>((free_b + sc.cap) / 2, 64ull << 30), 64ull << 20);
+    // (8 GB hold ~1 900 pairs of 4096 x 4096: more than one wave of warps; the buffer is allocated once and reused)
+    const uint64_t budget = std::max<uint64_t>(std::min<uint64_t>((free_b + sc.cap) / 2, 8ull << 30), 64ull << 20);
 
     PhaseTimer pt;
     uint64_t done = 0;

@@ -40,10 +40,17 @@ def lib():
         L.apd_emul_cells_visited.argtypes = [C.c_uint64] * 3
         L.apd_emul_window.restype = C.c_int
         L.apd_emul_window.argtypes = [C.c_float, C.c_int, C.c_int]
+        L.apd_emul_tile_cols.restype = None
+        L.apd_emul_tile_cols.argtypes = [C.c_int]
         L.apd_emul_force_rho.restype = None
         L.apd_emul_force_rho.argtypes = [C.c_int, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
+
+
+def tile_cols(tc):
+    """Tile width of the emulated lane program: 4 (8-warp kernels) or 2 (12-warp kernel)."""
+    lib().apd_emul_tile_cols(int(tc))
 
 
 def force_rho(rho):

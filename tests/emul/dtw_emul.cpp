@@ -19,7 +19,7 @@ using namespace apd;
 
 namespace {
 
-template <int DPAD>
+template <int DPAD, int TC>
 struct HostCtx {
     const LaneGeom* lanes;  // 32
     RowGeom rg;
@@ -59,11 +59,11 @@ struct HostCtx {
     void ring_wait(F2 (&)[TILE]) const {}
     void ring_store(int slot, const F2 (&v)[TILE]) { for (int r = 0; r < TILE; r++) state[slot * TILE + r] = v[r]; tiles++; }
     F2 ring_load_last(int slot) const { return state[slot * TILE + TILE - 1]; }
-    void switch_y(int J, F2 (&yv)[TILE][DPAD / 2]) const
+    void switch_y(int J, F2 (&yv)[TC][DPAD / 2]) const
     {
         if (J >= lanes[lane].Jt) return;
-        const float* p = ybase + (int64_t)(4 * J - lanes[lane].gamma - 1) * DPAD;
-        for (int c = 0; c < TILE; c++)
+        const float* p = ybase + (int64_t)(TC * J - lanes[lane].gamma - 1) * DPAD;
+        for (int c = 0; c < TC; c++)
             for (int k = 0; k < DPAD / 2; k++) yv[c][k] = mk2(p[c * DPAD + 2 * k], p[c * DPAD + 2 * k + 1]);
     }
     const float* stage[X_STAGES] = {nullptr, nullptr, nullptr, nullptr};
@@ -73,11 +73,12 @@ struct HostCtx {
 };
 
 static uint64_t exact_units = 0;
+static int g_tile_cols = 4;           // tests: 4 (the 8-warp kernels' tiles) or 2 (the 12-warp kernel's)
 static int g_force_rho = -1;          // tests: run every unit on one fixed row grid
 static uint64_t rho_used[4] = {0, 0, 0, 0};
 static uint64_t step_counts[3] = {0, 0, 0};
 
-template <int DPAD>
+template <int DPAD, int TC>
 int run_all(const Arena& ar, const UnitPlan& plan, float pct, Penalties pen, int strict,
             bool unitw, uint32_t rank, uint32_t world, float* out, uint64_t* tiles_out)
 {
@@ -94,7 +95,7 @@ int run_all(const Arena& ar, const UnitPlan& plan, float pct, Penalties pen, int
             for (int l = 0; l < 32; l++) {
                 uint32_t b = 32 * un.B + l;
                 bool exists = b > un.a && b < N;
-                lanes[l] = lane_geometry(exists, n, exists ? (int)ar.len[b] : 0, pct);
+                lanes[l] = lane_geometry(exists, n, exists ? (int)ar.len[b] : 0, pct, TC);
                 if (lanes[l].Jt > Jt_max) Jt_max = lanes[l].Jt;
                 if (lanes[l].active && lanes[l].w > wmax) wmax = lanes[l].w;
                 const unsigned int v = lane_rho_votes(lanes[l], n);
@@ -102,7 +103,7 @@ int run_all(const Arena& ar, const UnitPlan& plan, float pct, Penalties pen, int
             }
             RowGeom rg = row_geometry(n, g_force_rho >= 0 ? g_force_rho : choose_rho(votes, n));
             rho_used[rg.rho]++;
-            if (ring_tiles_needed(wmax, rg.It > 0 ? rg.It : 1) > uc.St) return -10;  // planner bug
+            if (ring_tiles_needed(wmax, rg.It > 0 ? rg.It : 1, TC) > uc.St) return -10;  // planner bug
             for (int l = 0; l < 32; l++) {
                 uint32_t b = 32 * un.B + l;
                 if (!(b > un.a && b < N)) continue;
@@ -111,7 +112,7 @@ int run_all(const Arena& ar, const UnitPlan& plan, float pct, Penalties pen, int
                 if (!lanes[l].active) {
                     s1 = s2 = INFINITY;  // src/alignments.rs:116-125 with an empty side
                 } else {
-                    HostCtx<DPAD> ctx;
+                    HostCtx<DPAD, TC> ctx;
                     ctx.lanes = lanes; ctx.rg = rg; ctx.lane = l;
                     ctx.steps = step_counts;
                     for (int q = 0; q < 32 && ctx.first_lane < 0; q++) if (lanes[q].active) ctx.first_lane = q;
@@ -122,17 +123,17 @@ int run_all(const Arena& ar, const UnitPlan& plan, float pct, Penalties pen, int
                     F2 acc;
                     SqrtFlags fl;
                     flags_reset(fl);
-                    if (strict && unitw) acc = run_unit<DPAD, true, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
-                    else if (strict) acc = run_unit<DPAD, true, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
-                    else if (unitw) acc = run_unit<DPAD, false, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
-                    else acc = run_unit<DPAD, false, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
+                    if (strict && unitw) acc = run_unit<DPAD, TC, true, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
+                    else if (strict) acc = run_unit<DPAD, TC, true, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
+                    else if (unitw) acc = run_unit<DPAD, TC, false, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
+                    else acc = run_unit<DPAD, TC, false, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen, fl);
                     // The host sqrt is exact everywhere, so the flags never change a result here;
                     // strict == 2 forces the cold path so that its schedule is exercised too.
                     if (strict == 2 || (strict && flags_bad(fl))) {
                         exact_units++;
                         ctx.state.assign((size_t)uc.St * TILE, poison);
-                        acc = unitw ? run_unit_exact<DPAD, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen)
-                                    : run_unit_exact<DPAD, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen);
+                        acc = unitw ? run_unit_exact<DPAD, TC, true>(ctx, lanes[l], rg, Jt_max, uc.St, pen)
+                                    : run_unit_exact<DPAD, TC, false>(ctx, lanes[l], rg, Jt_max, uc.St, pen);
                     }
                     if (ctx.mismatch) return -11;  // interior range formula disagrees with the tile predicate
                     s1 = finish_score(acc.x, n, m);
@@ -173,14 +174,22 @@ int apd_emul_align_all(const float* const* frames, const uint32_t* lens, uint32_
     uint64_t tiles = 0;
     int rc;
     switch (ar.dpad) {
-        case 4: rc = run_all<4>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
-        case 8: rc = run_all<8>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
-        case 12: rc = run_all<12>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
-        case 16: rc = run_all<16>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
-        case 20: rc = run_all<20>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
-        case 24: rc = run_all<24>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
-        case 28: rc = run_all<28>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
-        case 32: rc = run_all<32>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 4: rc = g_tile_cols == 2 ? run_all<4, 2>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles)
+                                         : run_all<4, 4>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 8: rc = g_tile_cols == 2 ? run_all<8, 2>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles)
+                                         : run_all<8, 4>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 12: rc = g_tile_cols == 2 ? run_all<12, 2>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles)
+                                         : run_all<12, 4>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 16: rc = g_tile_cols == 2 ? run_all<16, 2>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles)
+                                         : run_all<16, 4>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 20: rc = g_tile_cols == 2 ? run_all<20, 2>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles)
+                                         : run_all<20, 4>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 24: rc = g_tile_cols == 2 ? run_all<24, 2>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles)
+                                         : run_all<24, 4>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 28: rc = g_tile_cols == 2 ? run_all<28, 2>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles)
+                                         : run_all<28, 4>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
+        case 32: rc = g_tile_cols == 2 ? run_all<32, 2>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles)
+                                         : run_all<32, 4>(ar, plan, pct, pen, strict, unitw, rank, world, out_nxn, &tiles); break;
         default: return -3;
     }
     if (info) {
@@ -238,6 +247,9 @@ void apd_emul_force_rho(int rho, uint64_t* used4)
     if (used4) for (int r = 0; r < 4; r++) used4[r] = rho_used[r];
     for (int r = 0; r < 4; r++) rho_used[r] = 0;
 }
+
+// Tile width of the emulated lane program: 4 or 2 columns.
+void apd_emul_tile_cols(int tc) { g_tile_cols = (tc == 2) ? 2 : 4; }
 
 uint64_t apd_emul_cells_visited(uint64_t n, uint64_t m, uint64_t w) { return cells_visited(n, m, w); }
 

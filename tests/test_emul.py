@@ -191,3 +191,40 @@ def test_chosen_row_grid_needs_fewer_tiles_on_the_headline_shape():
     assert np.array_equal(bits(got0), bits(want)) and np.array_equal(bits(got), bits(want))
     assert used[0] == 0 and used.sum() > 0              # the anchored grid is not the one chosen here
     assert int(info[3]) < 0.975 * int(info0[3])         # >= 2.5 % fewer lane-tiles
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_two_column_tiles_match_oracle_bitwise(case):
+    """The 12-warps-per-SM kernel runs the same lane program on 4 x 2-column tiles."""
+    n, lo, hi, dim, pct, (ins, dele, mat), integer = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    seqs = random_sequences(rng, n, lo, hi, dim, integer)
+    want = oracle.align_all(seqs, pct, ins, dele, mat, workers=4, variant="dense")
+    try:
+        emul.tile_cols(2)
+        for strict in (1, 2):
+            got, info = emul.align_all(seqs, pct, ins, dele, mat, strict=strict)
+            assert np.array_equal(bits(got), bits(want)), strict
+        for rho in (0, 1, 2, 3):
+            emul.force_rho(rho)
+            got, _ = emul.align_all(seqs, pct, ins, dele, mat, strict=True)
+            assert np.array_equal(bits(got), bits(want)), rho
+    finally:
+        emul.force_rho(-1)
+        emul.tile_cols(4)
+
+
+@pytest.mark.parametrize("dim", [5, 13, 16, 24, 30, 32])
+def test_two_column_tiles_every_padded_frame_width(dim):
+    rng = np.random.default_rng(300 + dim)
+    seqs = random_sequences(rng, 14, 6, 40, dim, integer=(dim % 2 == 1))
+    want = oracle.align_all(seqs, 0.2, 0.75, 0.5, 1.0, variant="dense")
+    try:
+        emul.tile_cols(2)
+        got, _ = emul.align_all(seqs, 0.2, 0.75, 0.5, 1.0, strict=True)
+        gotf, _ = emul.align_all(seqs, 0.2, 0.75, 0.5, 1.0, strict=False)
+    finally:
+        emul.tile_cols(4)
+    assert np.array_equal(bits(got), bits(want))
+    off = ~np.eye(len(seqs), dtype=bool)
+    assert np.max(np.abs(gotf[off] - want[off]) / np.abs(want[off])) <= 1e-5
