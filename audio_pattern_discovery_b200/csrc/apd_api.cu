@@ -49,7 +49,7 @@ struct OccKey { int dpad, strict, unitw, ring; size_t smem; int occ; };
 struct DevStatus {            // device-side flags of one align call, read back in one copy
     int error;                // a unit needed a bigger ring than planned
     int pad;
-    unsigned long long tiles; // lane-tiles executed (statistics)
+    unsigned long long tiles; // lane-tile columns executed (statistics)
 };
 
 enum { STAGE_BUFS = 3, MAX_CLASSES = SMEM_RING_CAPS + 1 };
@@ -438,9 +438,11 @@ apd_status run_dtw(apd_ctx* m, const apd_params* p, float* const* outs, uint32_t
         // (a ring up to TMEM_SPILL_TILES taller than tensor memory holds spills its tail to shared memory
         // and still runs 2 CTAs x 4 warps per SM)
         if (ring_floor == RING_TMEM && uc.St <= TMEM_RING_TILES + TMEM_SPILL_TILES) q.ring = RING_TMEM;
-        // 12 warps per SM on 4 x 2-column tiles where the ring fits tensor memory outright
-        if (q.ring == RING_TMEM && L->wide && uc.St <= TMEM_RING_TILES) q.ring = RING_WIDE;
         else if (ring_floor != RING_GLOBAL && !uc.gstate) q.ring = RING_SMEM;
+        // APD_WIDE=1 (experiment, slower: profiles/README.md r2f): 12 warps per SM on 4 x 2-column tiles where the
+        // ring fits tensor memory outright and the frames are at most 24 wide (beyond that even two columns of y
+        // exceed the 168 registers three warps per scheduler leave)
+        if (q.ring == RING_TMEM && L->wide && uc.St <= TMEM_RING_TILES && ar.dpad <= 24) q.ring = RING_WIDE;
         q.smem = dtw_smem_bytes((int)ar.dpad, uc.St, q.ring);
         if (q.smem > m->smem_optin) return fail(m, APD_ERR_INTERNAL, "ring does not fit in shared memory");
         s = occupancy(m, f, (int)ar.dpad, strict, unitw, q.ring, q.smem, q.occ);
@@ -556,7 +558,7 @@ void collect_stats(apd_ctx* c)
         tiles += m->tiles; units += m->local_units; launches += m->launches;
     }
     c->stats.kernel_ms = kms; c->stats.scatter_ms = sms;
-    c->stats.cells_computed = tiles * TILE * TILE * 2;
+    c->stats.cells_computed = tiles * TILE * 2;   // tile columns x TILE rows x 2 orientations
     c->stats.units_local = units;
     c->stats.units_total = c->plan.units.size();
     c->stats.kernel_launches = launches;

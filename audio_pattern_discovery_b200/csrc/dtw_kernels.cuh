@@ -67,7 +67,7 @@ struct KernelArgs {
     uint32_t n_out;
     float2* gstate;        // GSTATE: gridDim.x rings of St*4*32 float2
     int* error_flag;       // set to 1 if a unit needs a bigger ring than St (planner bug)
-    unsigned long long* tiles_done;  // optional: lane-tiles executed (statistics)
+    unsigned long long* tiles_done;  // optional: lane-tile columns (TILE cells each) executed (statistics)
 };
 
 #if defined(__CUDACC__)
@@ -75,7 +75,14 @@ struct KernelArgs {
 enum { X_BAR_F4 = 2 };  // float4 slots holding the X_STAGES mbarriers behind the stage buffers
 enum { RING_SMEM = 0, RING_GLOBAL = 1, RING_TMEM = 2, RING_WIDE = 3 };
 enum { TMEM_WARPS = 4, TMEM_COLS = 256, TMEM_RING_TILES = TMEM_COLS / 8 };
-enum { TMEM_SPILL_TILES = 25 };  // slots of a RING_TMEM ring that may live in shared memory: 2 CTAs x 4 warps x 25 KB < 227 KB
+enum { TMEM_SPILL_TILES = 25 };
+// Tile width of the 8-warps-per-SM kernels: 4 columns of y in registers (DPAD/2 register pairs
+// each) -- 2 columns from 28-wide frames on, where 4 no longer fit the register file without
+// spilling (26 is the reference's raw cepstrum width, src/spectrogram.rs:76).
+template <int DPAD>
+struct TileCols {
+    static constexpr int value = DPAD >= 28 ? 2 : TILE;
+};  // slots of a RING_TMEM ring that may live in shared memory: 2 CTAs x 4 warps x 25 KB < 227 KB
 
 template <int DPAD, int RING, int TC = TILE>
 struct DevCtx {
@@ -351,7 +358,7 @@ APD_D void warp_unit_loop(const KernelArgs& a, DevCtx<DPAD, RING, TC>& ctx)
     }
     if (a.tiles_done) {
         unsigned int t = __reduce_add_sync(0xffffffffu, ctx.tiles);
-        if (lane == 0) atomicAdd(a.tiles_done, (unsigned long long)t);
+        if (lane == 0) atomicAdd(a.tiles_done, (unsigned long long)t * TC);   // in tile columns (TILE cells each)
     }
 }
 
@@ -361,7 +368,7 @@ __global__ void __launch_bounds__(32) dtw_units_kernel(const KernelArgs a)
 {
     extern __shared__ float4 smem4[];
     const int lane = threadIdx.x;
-    DevCtx<DPAD, RING> ctx;
+    DevCtx<DPAD, RING, TileCols<DPAD>::value> ctx;
     ctx.lane = lane;
     ctx.xs4 = smem4;
     ctx.xs_smem = (uint32_t)__cvta_generic_to_shared(smem4);
@@ -374,7 +381,7 @@ __global__ void __launch_bounds__(32) dtw_units_kernel(const KernelArgs a)
     ctx.St = a.St;
     ctx.tiles = 0;
     ctx.x_init();
-    warp_unit_loop<DPAD, STRICT, UNITW, RING, TILE>(a, ctx);
+    warp_unit_loop<DPAD, STRICT, UNITW, RING, TileCols<DPAD>::value>(a, ctx);
 }
 
 // RING_TMEM: CTAs of TMEM_WARPS independent warps sharing one tensor-memory allocation of
@@ -396,7 +403,7 @@ __global__ void __launch_bounds__(32 * TMEM_WARPS, 2) dtw_units_tmem_kernel(cons
     asm volatile("tcgen05.fence::after_thread_sync;\n");
     const uint32_t tmem_base = tmem_base_smem;
 
-    DevCtx<DPAD, RING_TMEM> ctx;
+    DevCtx<DPAD, RING_TMEM, TileCols<DPAD>::value> ctx;
     ctx.lane = lane;
     const int spill = a.St > TMEM_RING_TILES ? a.St - TMEM_RING_TILES : 0;   // ring slots kept in shared memory
     float4* wbase = smem4 + warp * (X_STAGES * DPAD + X_BAR_F4 + spill * 2 * 32);
@@ -409,7 +416,7 @@ __global__ void __launch_bounds__(32 * TMEM_WARPS, 2) dtw_units_tmem_kernel(cons
     ctx.St = a.St;
     ctx.tiles = 0;
     ctx.x_init();
-    warp_unit_loop<DPAD, STRICT, UNITW, RING_TMEM, TILE>(a, ctx);
+    warp_unit_loop<DPAD, STRICT, UNITW, RING_TMEM, TileCols<DPAD>::value>(a, ctx);
 
     asm volatile("tcgen05.fence::before_thread_sync;\n");
     __syncthreads();
