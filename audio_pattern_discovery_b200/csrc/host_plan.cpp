@@ -164,7 +164,7 @@ static inline void unit_cost(const Arena& ar, float pct, uint32_t a, uint32_t B,
 // counting sort over (class, cost bucket): the row sequences are dealt to host threads in
 // contiguous ranges, every thread histograms its units, a prefix sum over (bucket, thread)
 // gives each thread its private output cursor per bucket -- so the result is identical to the
-// serial order (a ascending, B ascending inside a bucket) whatever the thread count -- and a
+// serial enumeration order inside a bucket whatever the thread count -- and a
 // second pass writes the units.  10 000 sequences (1.57 M units): ~100 ms serial, ~15 ms on 8 threads;
 // this is on the critical path of the first align call.
 void build_unit_plan(const Arena& ar, float pct, UnitPlan& out)
@@ -181,19 +181,30 @@ void build_unit_plan(const Arena& ar, float pct, UnitPlan& out)
     unsigned nt = std::thread::hardware_concurrency();
     nt = std::max(1u, std::min(nt, 16u));
     if ((uint64_t)N * nblocks < (1u << 16)) nt = 1;
-    // contiguous ranges of `a` with about equal unit counts: units(a) = nblocks - (a+1)/32
-    std::vector<uint32_t> a_begin(nt + 1, 0);
+    // Enumeration order inside a cost bucket: blocks of 32 row sequences, then the column block B,
+    // then the row sequence inside its block -- 32 consecutive units share the 32 column sequences of
+    // B, so the ~1200 warps resident on a GPU work on a few dozen column blocks at a time (tens of MB,
+    // L2 resident) instead of streaming the whole arena past every row sequence (C3: 413 MB > L2).
+    // Row blocks are dealt to the host threads in contiguous ranges with about equal unit counts.
+    const uint32_t nrb = (N - 1 + 31) / 32;   // row sequences are 0 .. N-2
+    auto units_of_rb = [&](uint32_t rb) -> uint64_t {
+        uint64_t c = 0;
+        const uint32_t a1 = std::min(rb * 32 + 32, N - 1);
+        for (uint32_t a = rb * 32; a < a1; a++) c += nblocks - (a + 1) / 32;
+        return c;
+    };
+    std::vector<uint32_t> rb_begin(nt + 1, 0);
     {
         uint64_t total = 0;
-        for (uint32_t a = 0; a + 1 < N; a++) total += nblocks - (a + 1) / 32;
+        for (uint32_t rb = 0; rb < nrb; rb++) total += units_of_rb(rb);
         uint64_t acc = 0;
         unsigned t = 1;
-        for (uint32_t a = 0; a + 1 < N && t < nt; a++) {
-            acc += nblocks - (a + 1) / 32;
-            if (acc * nt >= total * t) a_begin[t++] = a + 1;
+        for (uint32_t rb = 0; rb < nrb && t < nt; rb++) {
+            acc += units_of_rb(rb);
+            if (acc * nt >= total * t) rb_begin[t++] = rb + 1;
         }
-        for (; t < nt; t++) a_begin[t] = N - 1;
-        a_begin[nt] = N - 1;
+        for (; t < nt; t++) rb_begin[t] = nrb;
+        rb_begin[nt] = nrb;
     }
     auto for_threads = [&](auto&& fn) {
         if (nt == 1) { fn(0u); return; }
@@ -201,20 +212,28 @@ void build_unit_plan(const Arena& ar, float pct, UnitPlan& out)
         for (unsigned t = 0; t < nt; t++) th.emplace_back([&fn, t] { fn(t); });
         for (auto& x : th) x.join();
     };
+    // visit(t, f): f(a, B) for every unit of thread t's row blocks, in enumeration order
+    auto visit = [&](unsigned t, auto&& f) {
+        for (uint32_t rb = rb_begin[t]; rb < rb_begin[t + 1]; rb++) {
+            const uint32_t a0 = rb * 32, a1 = std::min(a0 + 32, N - 1);
+            for (uint32_t B = (a0 + 1) / 32; B < nblocks; B++)
+                for (uint32_t a = a0; a < a1; a++)
+                    if (B >= (a + 1) / 32) f(a, B);
+        }
+    };
 
     // pass 1: maximum cost (bucket scale), per-class ring need and counts
     struct Acc { uint32_t max_cost = 1; int cls_need[SMEM_RING_CAPS + 1] = {0, 0, 0, 0}; uint64_t tiles = 0; };
     std::vector<Acc> acc(nt);
     for_threads([&](unsigned t) {
         Acc A;
-        for (uint32_t a = a_begin[t]; a < a_begin[t + 1]; a++)
-            for (uint32_t B = (a + 1) / 32; B < nblocks; B++) {
-                uint32_t cost; int cls, need;
-                unit_cost(ar, pct, a, B, cost, cls, need);
-                A.max_cost = std::max(A.max_cost, cost);
-                A.cls_need[cls] = std::max(A.cls_need[cls], need);
-                A.tiles += cost;
-            }
+        visit(t, [&](uint32_t a, uint32_t B) {
+            uint32_t cost; int cls, need;
+            unit_cost(ar, pct, a, B, cost, cls, need);
+            A.max_cost = std::max(A.max_cost, cost);
+            A.cls_need[cls] = std::max(A.cls_need[cls], need);
+            A.tiles += cost;
+        });
         acc[t] = A;
     });
     uint32_t max_cost = 1;
@@ -232,12 +251,11 @@ void build_unit_plan(const Arena& ar, float pct, UnitPlan& out)
     std::vector<std::vector<uint64_t>> hist(nt, std::vector<uint64_t>(n_bkt, 0));
     for_threads([&](unsigned t) {
         std::vector<uint64_t>& h = hist[t];
-        for (uint32_t a = a_begin[t]; a < a_begin[t + 1]; a++)
-            for (uint32_t B = (a + 1) / 32; B < nblocks; B++) {
-                uint32_t cost; int cls, need;
-                unit_cost(ar, pct, a, B, cost, cls, need);
-                h[bucket(cost, cls)]++;
-            }
+        visit(t, [&](uint32_t a, uint32_t B) {
+            uint32_t cost; int cls, need;
+            unit_cost(ar, pct, a, B, cost, cls, need);
+            h[bucket(cost, cls)]++;
+        });
     });
     // exclusive prefix over (bucket major, thread minor)
     uint64_t pos = 0;
@@ -253,13 +271,12 @@ void build_unit_plan(const Arena& ar, float pct, UnitPlan& out)
     // pass 3: write
     for_threads([&](unsigned t) {
         std::vector<uint64_t>& cur = hist[t];
-        for (uint32_t a = a_begin[t]; a < a_begin[t + 1]; a++)
-            for (uint32_t B = (a + 1) / 32; B < nblocks; B++) {
-                uint32_t cost; int cls, need;
-                unit_cost(ar, pct, a, B, cost, cls, need);
-                Unit u; u.a = a; u.B = B;
-                out.units[cur[bucket(cost, cls)]++] = u;
-            }
+        visit(t, [&](uint32_t a, uint32_t B) {
+            uint32_t cost; int cls, need;
+            unit_cost(ar, pct, a, B, cost, cls, need);
+            Unit u; u.a = a; u.B = B;
+            out.units[cur[bucket(cost, cls)]++] = u;
+        });
     });
     pos = 0;
     for (int c = 0; c < n_cls; c++) {
