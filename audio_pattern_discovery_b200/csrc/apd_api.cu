@@ -337,8 +337,10 @@ uint64_t packed_entries(const apd_ctx* c)
 apd_status ensure_plan(apd_ctx* c, float pct)
 {
     // The plan depends on pct only through the band (bit pattern compare keeps NaN stable).
-    if (!(c->plan_valid && std::memcmp(&c->plan.pct, &pct, sizeof(float)) == 0)) {
-        build_unit_plan(c->arena, pct, c->plan);
+    const uint32_t sharers = c->members.size() > 1 ? (uint32_t)c->members.size() : c->world;
+    const uint32_t row_block = 32u * std::min<uint32_t>(std::max<uint32_t>(sharers, 1u), 16u);
+    if (!(c->plan_valid && std::memcmp(&c->plan.pct, &pct, sizeof(float)) == 0 && c->plan.row_block == row_block)) {
+        build_unit_plan(c->arena, pct, c->plan, row_block);
         c->cells_ref_valid = false;
         c->plan_valid = true;
         c->plan_serial++;

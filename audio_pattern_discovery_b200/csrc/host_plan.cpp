@@ -167,10 +167,13 @@ static inline void unit_cost(const Arena& ar, float pct, uint32_t a, uint32_t B,
 // serial enumeration order inside a bucket whatever the thread count -- and a
 // second pass writes the units.  10 000 sequences (1.57 M units): ~100 ms serial, ~15 ms on 8 threads;
 // this is on the critical path of the first align call.
-void build_unit_plan(const Arena& ar, float pct, UnitPlan& out)
+void build_unit_plan(const Arena& ar, float pct, UnitPlan& out, uint32_t row_block)
 {
     out = UnitPlan();
     out.pct = pct;
+    if (row_block < 32) row_block = 32;
+    row_block = (row_block + 31) & ~31u;
+    out.row_block = row_block;
     const uint32_t N = ar.n;
     if (N < 2) return;
     const uint32_t nblocks = (N + 31) / 32;
@@ -181,16 +184,19 @@ void build_unit_plan(const Arena& ar, float pct, UnitPlan& out)
     unsigned nt = std::thread::hardware_concurrency();
     nt = std::max(1u, std::min(nt, 16u));
     if ((uint64_t)N * nblocks < (1u << 16)) nt = 1;
-    // Enumeration order inside a cost bucket: blocks of 32 row sequences, then the column block B,
-    // then the row sequence inside its block -- 32 consecutive units share the 32 column sequences of
-    // B, so the ~1200 warps resident on a GPU work on a few dozen column blocks at a time (tens of MB,
-    // L2 resident) instead of streaming the whole arena past every row sequence (C3: 413 MB > L2).
+    // Enumeration order inside a cost bucket: blocks of `row_block` row sequences, then the column
+    // block B, then the row sequence inside its block -- row_block consecutive units share the 32
+    // column sequences of B, so the ~1200 warps resident on a GPU work on a few dozen column blocks at
+    // a time (tens of MB, L2 resident) instead of streaming the whole arena past every row sequence
+    // (C3: 413 MB > L2).  row_block = 32 x (devices or ranks sharing the list): units are dealt
+    // u mod world, so every device still sees 32 consecutive units of its own per column block.
     // Row blocks are dealt to the host threads in contiguous ranges with about equal unit counts.
-    const uint32_t nrb = (N - 1 + 31) / 32;   // row sequences are 0 .. N-2
+    const uint32_t RB = row_block;
+    const uint32_t nrb = (N - 1 + RB - 1) / RB;   // row sequences are 0 .. N-2
     auto units_of_rb = [&](uint32_t rb) -> uint64_t {
         uint64_t c = 0;
-        const uint32_t a1 = std::min(rb * 32 + 32, N - 1);
-        for (uint32_t a = rb * 32; a < a1; a++) c += nblocks - (a + 1) / 32;
+        const uint32_t a1 = std::min(rb * RB + RB, N - 1);
+        for (uint32_t a = rb * RB; a < a1; a++) c += nblocks - (a + 1) / 32;
         return c;
     };
     std::vector<uint32_t> rb_begin(nt + 1, 0);
@@ -215,7 +221,7 @@ void build_unit_plan(const Arena& ar, float pct, UnitPlan& out)
     // visit(t, f): f(a, B) for every unit of thread t's row blocks, in enumeration order
     auto visit = [&](unsigned t, auto&& f) {
         for (uint32_t rb = rb_begin[t]; rb < rb_begin[t + 1]; rb++) {
-            const uint32_t a0 = rb * 32, a1 = std::min(a0 + 32, N - 1);
+            const uint32_t a0 = rb * RB, a1 = std::min(a0 + RB, N - 1);
             for (uint32_t B = (a0 + 1) / 32; B < nblocks; B++)
                 for (uint32_t a = a0; a < a1; a++)
                     if (B >= (a + 1) / 32) f(a, B);

@@ -56,13 +56,15 @@ struct UnitPlan {
     std::vector<Unit> units;        // ordered: class by class, expensive units first
     std::vector<UnitClass> classes;
     uint64_t tiles_estimate = 0;    // sum of the per-unit cost estimates (tiles)
+    uint32_t row_block = 32;        // enumeration granularity the list was built with (see build_unit_plan)
 };
 
 // Largest ring (in tiles) kept in shared memory; bigger units go to the gstate class.
 enum { SMEM_RING_CAPS = 3 };
 extern const int kSmemRingCaps[SMEM_RING_CAPS];
 
-void build_unit_plan(const Arena& arena, float pct, UnitPlan& out);
+// row_block: 32 x the number of devices / ranks that deal the list among themselves (u mod world).
+void build_unit_plan(const Arena& arena, float pct, UnitPlan& out, uint32_t row_block = 32);
 
 // Reference cell updates (src/alignments.rs:174-175 visit rule) of one ordered pair.
 uint64_t cells_visited(uint64_t n, uint64_t m, uint64_t w);

@@ -45,10 +45,12 @@ class ShardedAligner:
         """-> (n, n) float32 CUDA tensor holding the full matrix on this rank."""
         k = self.ctx.packed_len(pct, self.mode)
         if self._packed is None or self._packed.numel() != k:
+            self.stream.synchronize()      # an earlier call may still be using the buffers that are about to be replaced
             self._packed = torch.empty(k, dtype=torch.float32, device=self.device)
             self._gathered = (torch.empty(k * self.world, dtype=torch.float32, device=self.device)
                               if self.world > 1 else self._packed)
         if self._matrix is None or self._matrix.shape[0] != self.n:
+            self.stream.synchronize()
             self._matrix = torch.empty((self.n, self.n), dtype=torch.float32, device=self.device)
         stream = self.stream
         with torch.cuda.stream(stream):

@@ -40,6 +40,9 @@ def lib():
         L.apd_emul_cells_visited.argtypes = [C.c_uint64] * 3
         L.apd_emul_window.restype = C.c_int
         L.apd_emul_window.argtypes = [C.c_float, C.c_int, C.c_int]
+        L.apd_emul_plan_units.restype = C.c_uint64
+        L.apd_emul_plan_units.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.c_uint32, C.c_float, C.c_uint32,
+                                          C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64)]
         L.apd_emul_tile_cols.restype = None
         L.apd_emul_tile_cols.argtypes = [C.c_int]
         L.apd_emul_force_rho.restype = None
@@ -89,3 +92,16 @@ def plan_info(lens, dim, pct, rank=0, world=1):
     if rc:
         raise RuntimeError("planner check failed: %d" % rc)
     return info
+
+
+def plan_units(lens, dim, pct, row_block=32):
+    """The planner's ordered unit list as (a, B) rows, plus units per launch class."""
+    lens = np.ascontiguousarray(lens, dtype=np.uint32)
+    n = len(lens)
+    cap = n * ((n + 31) // 32) + 1
+    out = np.zeros(cap, dtype=np.uint64)
+    info = np.zeros(4, dtype=np.uint64)
+    k = lib().apd_emul_plan_units(lens.ctypes.data_as(C.POINTER(C.c_uint32)), n, dim, pct, row_block,
+                                  out.ctypes.data_as(C.POINTER(C.c_uint64)), cap, info.ctypes.data_as(C.POINTER(C.c_uint64)))
+    u = out[:k]
+    return np.stack([(u >> np.uint64(32)).astype(np.int64), (u & np.uint64(0xffffffff)).astype(np.int64)], axis=1), info

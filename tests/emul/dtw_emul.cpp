@@ -251,6 +251,20 @@ void apd_emul_force_rho(int rho, uint64_t* used4)
 // Tile width of the emulated lane program: 4 or 2 columns.
 void apd_emul_tile_cols(int tc) { g_tile_cols = (tc == 2) ? 2 : 4; }
 
+// The ordered unit list for a given enumeration block (row_block = 32 x sharers): units as (a << 32 | B),
+// at most cap entries; returns the number of units, classes via info[0..3] = units per class.
+uint64_t apd_emul_plan_units(const uint32_t* lens, uint32_t n, uint32_t dim, float pct, uint32_t row_block,
+                             uint64_t* out, uint64_t cap, uint64_t* info)
+{
+    Arena ar;
+    if (!build_arena_layout(lens, n, dim, ar).empty()) return 0;
+    UnitPlan plan;
+    build_unit_plan(ar, pct, plan, row_block);
+    for (uint64_t k = 0; k < plan.units.size() && k < cap; k++) out[k] = ((uint64_t)plan.units[k].a << 32) | plan.units[k].B;
+    if (info) for (size_t c = 0; c < 4; c++) info[c] = c < plan.classes.size() ? plan.classes[c].end - plan.classes[c].begin : 0;
+    return plan.units.size();
+}
+
 uint64_t apd_emul_cells_visited(uint64_t n, uint64_t m, uint64_t w) { return cells_visited(n, m, w); }
 
 int apd_emul_window(float pct, int n, int m) { return window_of(pct, n, m); }

@@ -79,3 +79,22 @@ def test_synthetic_workloads_are_deterministic_and_shaped():
     assert lens.min() >= 97 and lens.max() <= 1024 and c["pct"] == 0.05
     assert all(len(s) == 512 for s in synth.make_config("C3", 5)[1])
     assert all(len(s) == 4096 for s in synth.make_config("C5", 2)[1])
+
+
+def test_unit_list_is_the_same_set_for_every_enumeration_block():
+    """The planner enumerates units in blocks of 32 x sharers rows (L2 locality per device); the block size
+    may only permute the list inside a class: same units, same classes, and row_block consecutive units of
+    one cost bucket share their column block."""
+    from .emul import plan_units
+    rng = np.random.default_rng(12)
+    lens = np.concatenate([np.full(700, 96), rng.integers(1, 300, size=200)])
+    base, info0 = plan_units(lens, 20, 0.1, 32)
+    key = lambda u: set(map(tuple, u.tolist()))
+    assert len(key(base)) == len(base)                      # no duplicates
+    for rb in (64, 256, 512):
+        u, info = plan_units(lens, 20, 0.1, rb)
+        assert key(u) == key(base) and np.array_equal(info, info0)
+    # equal-length sequences: one bucket, so the enumeration order is visible directly
+    u, _ = plan_units(np.full(2000, 128), 20, 0.1, 128)
+    runs = np.flatnonzero(np.diff(u[:, 1]) != 0)
+    assert np.median(np.diff(runs)) == 128                  # 128 consecutive units per column block
