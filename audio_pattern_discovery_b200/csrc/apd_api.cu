@@ -121,6 +121,7 @@ struct apd_ctx {
     int ring_floor = RING_TMEM;              // APD_RING / APD_FORCE_GSTATE, read once at creation
     bool debug = false;                      // APD_DEBUG
     bool concurrent_classes = true;          // APD_SERIAL_CLASSES=1 turns it off
+    bool uniform_carveout = true;            // APD_CARVEOUT=0 turns it off (see run_dtw)
     bool wide = false;                       // APD_WIDE: the 12-warps-per-SM kernel where the ring fits tensor memory
 
     apd_stats stats{};
@@ -457,6 +458,13 @@ apd_status run_dtw(apd_ctx* m, const apd_params* p, float* const* outs, uint32_t
     if (s != APD_OK) return s;
 
     m->launch_desc.clear();
+    // Kernels whose shared-memory needs differ run with different L1 / shared-memory splits, and an SM does not
+    // change its split while CTAs of the other kind are resident -- the classes of one call would run one after
+    // the other.  When a call launches more than one class they all ask for the same (maximum shared) split.
+    int active_classes = 0;
+    for (size_t ci = 0; ci < ncls; ci++) active_classes += (cls[ci].k1 > cls[ci].k0) ? 1 : 0;
+    const int carveout = (L->uniform_carveout && L->concurrent_classes && active_classes > 1) ? (int)cudaSharedmemCarveoutMaxShared
+                                                                                             : (int)cudaSharedmemCarveoutDefault;
     const bool fork = L->concurrent_classes && ncls > 1;
     if (fork) APD_CUDA(m, cudaEventRecord(m->ev_fork, stream));
     size_t gstate_used = 0;
@@ -476,6 +484,7 @@ apd_status run_dtw(apd_ctx* m, const apd_params* p, float* const* outs, uint32_t
         a.St = uc.St;
         for (uint32_t o = 0; o < n_out; o++) a.out[o] = reinterpret_cast<float2*>(outs[o]);
         a.n_out = n_out;
+        a.carveout = carveout;
         a.error_flag = &m->d_status->error;
         a.tiles_done = &m->d_status->tiles;
         if (q.ring == RING_GLOBAL) {
@@ -668,6 +677,8 @@ apd_status create_one(int device_id, apd_ctx** out)
     c->debug = getenv("APD_DEBUG") != nullptr;
     const char* ser = getenv("APD_SERIAL_CLASSES");
     c->concurrent_classes = !(ser && ser[0] == '1');
+    const char* cv = getenv("APD_CARVEOUT");
+    c->uniform_carveout = !(cv && cv[0] == '0');
     const char* wide = getenv("APD_WIDE");
     c->wide = wide ? (wide[0] == '1') : false;
     c->stats.sm_clock_mhz = c->sm_clock_mhz;

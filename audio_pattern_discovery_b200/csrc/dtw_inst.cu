@@ -19,6 +19,8 @@ static cudaError_t launch_one(const KernelArgs& a, int grid, size_t smem, cudaSt
         auto kern = dtw_units_wide_kernel<APD_DPAD, STRICT, UNITW>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, a.carveout);
+        if (e != cudaSuccess) return e;
         kern<<<grid, 32 * WIDE_WARPS, smem, stream>>>(a);
         return cudaGetLastError();
     }
@@ -26,11 +28,15 @@ static cudaError_t launch_one(const KernelArgs& a, int grid, size_t smem, cudaSt
         auto kern = dtw_units_tmem_kernel<APD_DPAD, STRICT, UNITW>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, a.carveout);
+        if (e != cudaSuccess) return e;
         kern<<<grid, 32 * TMEM_WARPS, smem, stream>>>(a);
         return cudaGetLastError();
     }
     auto kern = dtw_units_kernel<APD_DPAD, STRICT, UNITW, (RING == RING_TMEM || RING == RING_WIDE) ? RING_SMEM : RING>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, a.carveout);
     if (e != cudaSuccess) return e;
     kern<<<grid, 32, smem, stream>>>(a);
     return cudaGetLastError();

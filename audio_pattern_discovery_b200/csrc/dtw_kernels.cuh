@@ -68,6 +68,7 @@ struct KernelArgs {
     float2* gstate;        // GSTATE: gridDim.x rings of St*4*32 float2
     int* error_flag;       // set to 1 if a unit needs a bigger ring than St (planner bug)
     unsigned long long* tiles_done;  // optional: lane-tile columns (TILE cells each) executed (statistics)
+    int carveout;          // host side only: preferred shared-memory carve-out of the launch (percent, -1 = driver default)
 };
 
 #if defined(__CUDACC__)
