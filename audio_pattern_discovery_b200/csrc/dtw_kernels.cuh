@@ -1,13 +1,15 @@
 // dtw_kernels.cuh -- sm_100a kernels of the all-pairs banded DTW (K1 of SURVEY.md
 // section 2.1) built around the lane program of dtw_core.h.
 //
-// Launch shape: persistent grid of single-warp CTAs (grid = SMs x resident CTAs per
-// SM, the latter set by the ring's shared-memory footprint), each warp pulling
-// 32-pair work units from an atomic counter in LPT order.
+// Launch shape: persistent grid (grid = SMs x resident CTAs per SM; CTAs of 4 independent
+// warps when the boundary ring lives in tensor memory, single-warp CTAs otherwise), each warp
+// pulling 32-pair work units from an atomic counter in LPT order.  The results of a unit are
+// stored to every buffer of KernelArgs::out -- in a single-process device group these are the
+// gathered buffers of all member GPUs, written through NVLink peer mappings.
 //
 // Data layout (see host_plan.h): one arena of zero-padded DPAD-float frames, every
 // frame 16-byte aligned, sequences sorted by length.  Per warp in shared memory:
-//   xs   : 4 x (4 frames x DPAD floats)  stage of the shared row sequence x, three tiles
+//   xs   : 4 x (4 frames x DPAD floats)  stage of the shared row sequence x, two tiles
 //          ahead of the recurrence: asynchronous 16-byte copies (cp.async -> LDGSTS), one
 //          group per tile, read back as warp-broadcast LDS.128 (a TMA bulk-copy variant is
 //          kept behind APD_X_STAGE_TMA; it measured slower)
@@ -25,8 +27,8 @@
 //                shared memory (same layout as RING_SMEM), which still leaves room for 2 CTAs
 //                of 4 warps per SM -- 8 resident warps instead of the 3-4 of a pure
 //                shared-memory ring.
-//   RING_SMEM    in shared memory (layout above), single-warp CTAs; bands too tall for
-//                256 TMEM columns.
+//   RING_SMEM    in shared memory (layout above), single-warp CTAs; only when tensor memory
+//                is ruled out (APD_RING=smem).
 //   RING_GLOBAL  in a per-warp slice of a global scratch buffer (same layout, coalesced
 //                512-byte rows, L2 resident); bands too tall for shared memory.
 #pragma once
@@ -118,14 +120,14 @@ struct DevCtx {
         return xbase4 + (ptrdiff_t)(4 * I - rg.rho - 1) * (DPAD / 4) + lane;
     }
 #if APD_X_STAGE_TMA
-    // EXPERIMENT (-DAPD_X_STAGE_TMA=1): x rows staged with the TMA unit's 1-D bulk copy
-    // (cp.async.bulk, SASS UBLKCP): one elected lane arms the buffer's mbarrier with the byte
+    // EXPERIMENT (-DAPD_X_STAGE_TMA=1, build.py --variant tma): x rows staged with the TMA unit's 1-D bulk
+    // copy (cp.async.bulk, SASS UBLKCP): one elected lane arms the buffer's mbarrier with the byte
     // count and issues the copy of the tile's 4 contiguous frames; readers wait on the phase
-    // parity.  Correct (GPU parity suite green) but measured SLOWER on the headline workload:
-    // 1073 -> 944 GCUPS (FAST), 729 -> 610 (STRICT) at C3/n=2000 with 2- and 3-tile lookahead
-    // alike -- the ~90-cycle mbarrier.try_wait round trip (B300_MICROARCH: TRYWAIT 90 when
-    // already complete) is exposed once per tile by in-order issue, and the bulk copy bypasses
-    // L1 where re-read x rows otherwise hit.  Kept for reference; the default is cp.async below.
+    // parity.  Correct (GPU parity suite green) but measured 12 % SLOWER on the headline shape
+    // (profiles/r2i_*TMA_staging_variant*: 669 vs 758 GCUPS STRICT, 926 vs 1131 FAST; FMA pipe 62.6 %
+    // vs 69.0 %, stall_wait 0.79 vs 0.56 per issue): the ~90-cycle mbarrier.try_wait round trip is
+    // exposed once per tile by in-order issue, and the bulk copy bypasses L1 where re-read x rows
+    // otherwise hit.  Kept for reference; the default is cp.async below.
     APD_D void x_fetch(int I, int buf, bool valid)
     {
         __syncwarp();
