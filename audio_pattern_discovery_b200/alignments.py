@@ -201,15 +201,23 @@ class Context:
         return v.value
 
     def align_packed(self, pct, ins, dele, mat, mode, d_packed_ptr, stream=0):
+        """Enqueues this shard's DTW kernels on `stream` (a cudaStream_t handle).  stream=0 is NOT the legacy
+        default stream: it selects the context's own private non-blocking stream, which has no implicit ordering
+        with torch's or any other stream -- pass your own stream (as ShardedAligner does) or call synchronize()
+        before another stream touches the buffers.  Calls on one context are ordered among themselves on the
+        device whatever streams they name."""
         p = _c_params(pct, ins, dele, mat, mode)
         self._check(self._lib.apd_align_packed(self._h, C.byref(p), C.c_void_p(d_packed_ptr),
                                                C.c_void_p(stream)))
 
     def scatter_packed(self, d_gathered_ptr, world, d_out_ptr, stream=0):
+        """Expands `world` gathered shards into the n x n device matrix on `stream` (0 = the context's own
+        private stream, see align_packed)."""
         self._check(self._lib.apd_scatter_packed(self._h, C.c_void_p(d_gathered_ptr), world,
                                                  C.c_void_p(d_out_ptr), C.c_void_p(stream)))
 
     def synchronize(self, stream=0):
+        """Waits for `stream` (0 = the context's own), collects kernel timings, checks the device error flag."""
         self._check(self._lib.apd_synchronize(self._h, C.c_void_p(stream)))
 
     def align_pairs(self, pairs, pct=1.0, ins=1.0, dele=1.0, mat=1.0, mode=APD_MODE_STRICT,

@@ -103,6 +103,44 @@ __device__ __forceinline__ float cell_distance(const F2 (&x)[DPAD / 2], const F2
     return sqrt_fast(d2);
 }
 
+// The 4 distances of one tile column (4 x rows against one y frame).  STRICT / FAST: dimension-major with
+// one accumulator per row, so four independent add chains are in flight (the per-cell operation order --
+// and therefore every bit -- is that of cell_distance()).
+template <int DPAD, int MODE>
+__device__ __forceinline__ void column_distances(const F2 (&xr)[TILE][DPAD / 2], const F2 (&y)[DPAD / 2], float (&d)[TILE])
+{
+    if (MODE == DIST_STRICT) {
+        float acc[TILE];
+#pragma unroll
+        for (int k = 0; k < DPAD / 2; k++) {
+            F2 p[TILE];
+#pragma unroll
+            for (int r = 0; r < TILE; r++) { const F2 t = sub2_rn(xr[r][k], y[k]); p[r] = mul2_rn(t, t); }
+#pragma unroll
+            for (int r = 0; r < TILE; r++) acc[r] = (k == 0) ? p[r].x : add_rn(acc[r], p[r].x);
+#pragma unroll
+            for (int r = 0; r < TILE; r++) acc[r] = add_rn(acc[r], p[r].y);
+        }
+#pragma unroll
+        for (int r = 0; r < TILE; r++) d[r] = sqrt_rn(acc[r]);
+    } else if (MODE == DIST_FAST) {
+        F2 acc2[TILE];
+#pragma unroll
+        for (int k = 0; k < DPAD / 2; k++) {
+#pragma unroll
+            for (int r = 0; r < TILE; r++) {
+                const F2 t = sub2_rn(xr[r][k], y[k]);
+                acc2[r] = (k == 0) ? mul2_rn(t, t) : fma2_rn(t, t, acc2[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < TILE; r++) d[r] = sqrt_fast(acc2[r].x + acc2[r].y);
+    } else {
+#pragma unroll
+        for (int r = 0; r < TILE; r++) d[r] = cell_distance<DPAD, MODE>(xr[r], y);
+    }
+}
+
 template <int DPAD, int MODE>
 __global__ void __launch_bounds__(32 * PW_WARPS) pair_wave_kernel(const WaveArgs a)
 {
@@ -249,11 +287,13 @@ __global__ void __launch_bounds__(32 * PW_WARPS) pair_wave_kernel(const WaveArgs
                                 yv[2 * v + 1] = sub2_rn(yv[2 * v + 1], ctr[2 * v + 1]);
                             }
                         }
+                        float dcol[TILE];
+                        column_distances<DPAD, MODE>(xr, yv, dcol);
                         float up = top[c];
                         float dg = (c == 0) ? diag : top[c - 1];
 #pragma unroll
                         for (int r = 0; r < TILE; r++) {
-                            const float d = cell_distance<DPAD, MODE>(xr[r], yv);
+                            const float d = dcol[r];
                             const float E = colprev[r];   // (i, j-1)   deletion
                             const float I = up;           // (i-1, j)   insertion
                             const float M = dg;           // (i-1, j-1) match
