@@ -121,3 +121,29 @@ def test_group_c3_shape_equals_single_device():
         grp.set_sequences(seqs)
         b = grp.align_all(c["pct"])
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_group_takes_every_upload_form():
+    """Flat upload (device-side gather) and encoded upload (auto-encoder on the device) on a device group:
+    the leader builds the arena, the other members pull it over NVLink."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from audio_pattern_discovery_b200 import AlignmentWorkers, Context, Discovery
+    rng = np.random.default_rng(17)
+    w = ((rng.random((26, 10)) - 0.5) / 10 * 6).astype(np.float32)
+    b = ((rng.random(10) - 0.5) / 10).astype(np.float32)
+    ceps = [(np.cumsum(rng.normal(size=(int(t), 26)), axis=0) * 0.4).astype(np.float32) for t in rng.integers(20, 90, size=70)]
+    emb = [oracle.ae_encode(x, w, b) for x in ceps]
+    want = oracle.align_all(emb, 1.0, 1.0, 1.0, 1.0, workers=8, variant="dense")
+    with Context(devices="all") as ctx:
+        ctx.set_sequences_encoded(ceps, w, b)
+        got = ctx.align_all(1.0)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        flat = np.concatenate([e.reshape(-1) for e in emb])
+        offs = np.cumsum([0] + [e.size for e in emb[:-1]])
+        ctx.set_sequences_flat(flat, offs, [len(e) for e in emb], 10)
+        got = ctx.align_all(1.0)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    wk = AlignmentWorkers.new_encoded(ceps, w, b)
+    wk.align_all(Discovery(warping_band_percentage=1.0))
+    assert np.array_equal(wk.result.lock().unwrap().reshape(70, 70).view(np.uint32), want.view(np.uint32))
