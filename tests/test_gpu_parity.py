@@ -419,3 +419,35 @@ def test_dim_above_the_supported_maximum_is_refused():
         with pytest.raises(ApdError) as ei:
             c.set_sequences([np.zeros((4, 33), np.float32)] * 2)
         assert ei.value.status == 4  # APD_ERR_UNSUPPORTED
+
+
+def test_hybrid_ring_and_launch_plan():
+    """A band taller than the 32 ring tiles tensor memory holds per warp keeps the ring's tail in shared
+    memory (still 2 CTAs x 4 warps per SM); the launch plan says where each class keeps its ring."""
+    from audio_pattern_discovery_b200 import Context
+    rng = np.random.default_rng(41)
+    seqs = [rng.normal(size=(int(t), 20)).astype(np.float32) for t in rng.integers(150, 200, size=70)]
+    want = oracle.align_all(seqs, 1.0, 0.75, 0.5, 1.0, workers=8, variant="dense")       # unbanded: ring = all row tiles
+    with Context(0) as c:
+        c.set_sequences(seqs)
+        got = c.align_all(1.0, 0.75, 0.5, 1.0)
+        plan = c.launch_plan()
+        gotu = c.align_all(1.0)
+    assert np.array_equal(bits(got), bits(want))
+    assert np.array_equal(bits(gotu), bits(oracle.align_all(seqs, 1.0, workers=8, variant="dense")))
+    assert any(p["ring"] == "tmem+smem" and 32 < p["ring_tiles"] <= 57 and p["ctas_per_sm"] == 2 for p in plan), plan
+
+
+def test_wide_kernel_experiment_is_bit_exact(monkeypatch):
+    """APD_WIDE=1: the 12-warps-per-SM kernel on 4 x 2-column tiles (measured slower, kept as an experiment)."""
+    from audio_pattern_discovery_b200 import Context
+    monkeypatch.setenv("APD_WIDE", "1")
+    rng = np.random.default_rng(43)
+    seqs = random_sequences(rng, 90, 40, 120, 20)
+    want = oracle.align_all(seqs, 0.1, workers=8, variant="dense")
+    with Context(0) as c:
+        c.set_sequences(seqs)
+        got = c.align_all(0.1)
+        plan = c.launch_plan()
+    assert np.array_equal(bits(got), bits(want))
+    assert any("12 warps" in p["ring"] for p in plan), plan
