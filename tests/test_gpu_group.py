@@ -147,3 +147,23 @@ def test_group_takes_every_upload_form():
     wk = AlignmentWorkers.new_encoded(ceps, w, b)
     wk.align_all(Discovery(warping_band_percentage=1.0))
     assert np.array_equal(wk.result.lock().unwrap().reshape(70, 70).view(np.uint32), want.view(np.uint32))
+
+
+def test_group_tiny_inputs():
+    """Fewer sequences than devices, empty and one-frame sequences: every member still takes part in the call."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from audio_pattern_discovery_b200 import Context
+    rng = np.random.default_rng(23)
+    with Context(devices="all") as ctx:
+        for lens in ([], [5], [5, 7], [0, 4, 1], [3, 3, 3, 1, 0, 9]):
+            seqs = [rng.normal(size=(t, 6)).astype(np.float32) for t in lens]
+            ctx.set_sequences(seqs, dim=6)
+            got = ctx.align_all(0.5, 0.75, 0.5, 1.0)
+            n = len(lens)
+            assert got.shape == (n, n)
+            if n >= 2:
+                want = oracle.align_all(seqs, 0.5, 0.75, 0.5, 1.0, workers=2, variant="dense")
+                assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), lens
+            elif n == 1:
+                assert got[0, 0] == 0.0
