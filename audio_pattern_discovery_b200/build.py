@@ -27,7 +27,7 @@ DPADS = (4, 8, 12, 16, 20, 24, 28, 32)
 CUDA_UNITS = ("apd_api", "pair_path", "percentile", "ae_encode")
 CXX_UNITS = ("host_plan", "upgma", "matrix_io")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ARCH + ["-D%s=%s" % (k, os.environ[k]) for k in ("APD_X_LOOK", "APD_USE_EDGE_VARIANT", "APD_X_STAGE_TMA", "APD_COMPACT", "APD_WEIGHTED_EDGE") if os.environ.get(k)] + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fno-fast-math,-ffp-contract=off"]
+NVCC_FLAGS = ARCH + ["-D%s=%s" % (k, os.environ[k]) for k in ("APD_X_LOOK", "APD_USE_EDGE_VARIANT", "APD_X_STAGE_TMA", "APD_COMPACT", "APD_WEIGHTED_EDGE", "APD_TWO_ROW_STEPS") if os.environ.get(k)] + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fno-fast-math,-ffp-contract=off"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-pthread", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Wno-unknown-pragmas"]
 
 

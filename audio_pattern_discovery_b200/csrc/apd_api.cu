@@ -122,7 +122,7 @@ struct apd_ctx {
     bool debug = false;                      // APD_DEBUG
     bool concurrent_classes = true;          // APD_SERIAL_CLASSES=1 turns it off
     bool uniform_carveout = true;            // APD_CARVEOUT=0 turns it off (see run_dtw)
-    bool wide = false;                       // APD_WIDE: the 12-warps-per-SM kernel where the ring fits tensor memory
+    int wide = -1;                           // APD_WIDE: 1 / 0 force the 12-warps-per-SM kernel on / off, unset = by penalties
 
     apd_stats stats{};
     std::string err;
@@ -442,10 +442,13 @@ apd_status run_dtw(apd_ctx* m, const apd_params* p, float* const* outs, uint32_t
         // and still runs 2 CTAs x 4 warps per SM)
         if (ring_floor == RING_TMEM && uc.St <= TMEM_RING_TILES + TMEM_SPILL_TILES) q.ring = RING_TMEM;
         else if (ring_floor != RING_GLOBAL && !uc.gstate) q.ring = RING_SMEM;
-        // APD_WIDE=1 (experiment, slower: profiles/README.md r2f): 12 warps per SM on 4 x 2-column tiles where the
-        // ring fits tensor memory outright and the frames are at most 24 wide (beyond that even two columns of y
-        // exceed the 168 registers three warps per scheduler leave)
-        if (q.ring == RING_TMEM && L->wide && uc.St <= TMEM_RING_TILES && ar.dpad <= 24) q.ring = RING_WIDE;
+        // 12 warps per SM on 4 x 2-column tiles (dtw_units_wide_kernel) where the ring fits tensor memory outright
+        // and the frames are at most 24 wide (beyond that even two columns of y exceed the 168 registers three
+        // warps per scheduler leave).  Measured (profiles/README.md, r2t): the weighted recurrence is bound by
+        // dependent-issue latency and gains 11 % from the third warp (C2 524 -> 581 GCUPS); with unit penalties
+        // the 8-warp kernel is 1 % ahead (C3 758 vs 751), so that is the default policy.  APD_WIDE=0|1 overrides.
+        const bool use_wide = L->wide == 1 || (L->wide < 0 && !unitw);
+        if (q.ring == RING_TMEM && use_wide && uc.St <= TMEM_RING_TILES && ar.dpad <= 24) q.ring = RING_WIDE;
         q.smem = dtw_smem_bytes((int)ar.dpad, uc.St, q.ring);
         if (q.smem > m->smem_optin) return fail(m, APD_ERR_INTERNAL, "ring does not fit in shared memory");
         s = occupancy(m, f, (int)ar.dpad, strict, unitw, q.ring, q.smem, q.occ);
@@ -680,7 +683,7 @@ apd_status create_one(int device_id, apd_ctx** out)
     const char* cv = getenv("APD_CARVEOUT");
     c->uniform_carveout = !(cv && cv[0] == '0');
     const char* wide = getenv("APD_WIDE");
-    c->wide = wide ? (wide[0] == '1') : false;
+    c->wide = wide ? (wide[0] == '1' ? 1 : 0) : -1;
     c->stats.sm_clock_mhz = c->sm_clock_mhz;
     c->stats.sm_count = (uint32_t)c->sm_count;
     c->members.push_back(c);
