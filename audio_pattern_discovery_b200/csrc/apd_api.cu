@@ -84,7 +84,8 @@ struct apd_ctx {
     float2* d_gstate = nullptr; size_t gstate_cap = 0;
     unsigned int* d_counters = nullptr;                  // one work counter per launch class
     DevStatus* d_status = nullptr;
-    DevStatus* h_status = nullptr;                       // pinned
+    DevStatus h_status_buf{};                            // read back with one small copy per call (pageable: pinning
+    DevStatus* h_status = &h_status_buf;                 // 16 bytes would cost more at creation than it ever saves)
     unsigned long long* d_hist = nullptr;                // 256 radix-select counters
     PathScratch path_scratch;                            // trace-back scratch (apd_align_pair(s)), grow-only
 
@@ -664,7 +665,6 @@ apd_status create_one(int device_id, apd_ctx** out)
     APD_CREATE_CUDA(cudaMalloc((void**)&c->d_counters, 8 * sizeof(unsigned int)));
     APD_CREATE_CUDA(cudaMalloc((void**)&c->d_status, sizeof(DevStatus)));
     APD_CREATE_CUDA(cudaMemset(c->d_status, 0, sizeof(DevStatus)));
-    APD_CREATE_CUDA(cudaMallocHost((void**)&c->h_status, sizeof(DevStatus)));
     APD_CREATE_CUDA(cudaMalloc((void**)&c->d_hist, 256 * sizeof(unsigned long long)));
     cudaEvent_t* evs[] = {&c->ev_k0, &c->ev_k1, &c->ev_s0, &c->ev_s1, &c->ev_h0, &c->ev_h1, &c->ev_d0, &c->ev_d1};
     for (cudaEvent_t* ev : evs) APD_CREATE_CUDA(cudaEventCreate(ev));
@@ -704,7 +704,6 @@ void destroy_one(apd_ctx* c)
                      c->d_matrix, c->d_gstate, c->d_counters, c->d_status, c->d_hist};
     for (void* p : dptrs) if (p) cudaFree(p);
     c->path_scratch.release();
-    if (c->h_status) cudaFreeHost(c->h_status);
     release_stage_ring(c);
     for (int b = 0; b < STAGE_BUFS; b++)
         if (c->ev_stage[b]) cudaEventDestroy(c->ev_stage[b]);
