@@ -89,6 +89,9 @@ PROTOTYPES = {
     "apd_set_sequences_encoded": (C.c_int, [C.c_void_p, C.POINTER(_fp), _u32p, C.c_uint32, C.c_uint32, _fp, _fp,
                                            C.c_uint32]),
     "apd_get_sequence": (C.c_int, [C.c_void_p, C.c_uint32, _fp, C.c_uint64]),
+    "apd_set_sequences_layout": (C.c_int, [C.c_void_p, _u32p, C.c_uint32, C.c_uint32]),
+    "apd_arena_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _u64p]),
+    "apd_arena_commit": (C.c_int, [C.c_void_p]),
     "apd_set_shard": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "apd_align_all": (C.c_int, [C.c_void_p, _pp, C.c_void_p]),
     "apd_packed_len": (C.c_int, [C.c_void_p, _pp, _u64p]),

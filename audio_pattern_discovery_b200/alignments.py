@@ -171,6 +171,22 @@ class Context:
         self._check(self._lib.apd_get_sequence(self._h, int(index), out.ctypes.data_as(_fp), out.size))
         return out
 
+    def set_sequences_layout(self, lens, dim):
+        """Declares a batch by its lengths and frame width only (one-process-per-GPU jobs: another rank uploads the
+        frames and this one receives the packed arena over NVLink, see arena_device / arena_commit)."""
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        self._check(self._lib.apd_set_sequences_layout(self._h, lens.ctypes.data_as(_u32p), len(lens), int(dim)))
+        self.n, self.dim = len(lens), int(dim)
+
+    def arena_device(self):
+        """-> (device pointer, floats) of the packed arena."""
+        ptr, n = C.c_void_p(0), C.c_uint64(0)
+        self._check(self._lib.apd_arena_device(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value or 0, n.value
+
+    def arena_commit(self):
+        self._check(self._lib.apd_arena_commit(self._h))
+
     def set_sequences_flat(self, flat, offsets, lens, dim):
         flat = np.ascontiguousarray(flat, dtype=np.float32)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)

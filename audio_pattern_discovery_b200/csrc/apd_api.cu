@@ -112,6 +112,7 @@ struct apd_ctx {
     // ---- host-side state (leader / single) -------------------------------------------------
     Arena arena;                             // layout only (data lives on the device)
     bool have_sequences = false;
+    bool arena_pending = false;              // layout declared, contents to be filled by the caller (apd_set_sequences_layout)
     UnitPlan plan; bool plan_valid = false; uint64_t plan_serial = 0;
     uint64_t cells_ref = 0; bool cells_ref_valid = false;
     bool matrix_valid = false;               // d_matrix (of the leader) holds the last apd_align_all result
@@ -273,6 +274,7 @@ apd_status begin_sequences(apd_ctx* c, const uint32_t* lens, uint32_t n, uint32_
     if (n > 0 && !lens) return fail(c, APD_ERR_INVALID, "lens is NULL");
     const bool had = c->have_sequences;
     c->have_sequences = false;
+    c->arena_pending = false;
     c->matrix_valid = false;
     Arena next;
     std::string e = build_arena_layout(lens, n, dim, next);
@@ -1002,6 +1004,37 @@ apd_status apd_set_sequences_encoded(apd_ctx* c, const float* const* cepstra, co
     s = broadcast_arena(c);
     if (s != APD_OK) return s;
     APD_CUDA(c, cudaStreamSynchronize(c->stream));  // src_sorted goes out of scope
+    c->have_sequences = true;
+    return APD_OK;
+}
+
+apd_status apd_set_sequences_layout(apd_ctx* c, const uint32_t* lens, uint32_t n, uint32_t dim)
+{
+    apd_status s = begin_sequences(c, lens, n, dim);
+    if (s != APD_OK) return s;
+    if (grouped(c)) return fail(c, APD_ERR_UNSUPPORTED, "a device group uploads once and copies over NVLink itself");
+    s = upload_tables(c, nullptr);
+    if (s != APD_OK) return s;
+    set_sequence_stats(c, n, 0);
+    c->arena_pending = true;   // the caller fills the arena (apd_arena_device) and then calls apd_arena_commit
+    return guard_end(c, c->stream);
+}
+
+apd_status apd_arena_device(apd_ctx* c, void** d_arena, uint64_t* n_floats)
+{
+    if (!c || !d_arena || !n_floats) return APD_ERR_INVALID;
+    if (c->lead != c || grouped(c)) return fail(c, APD_ERR_UNSUPPORTED, "one-device contexts only");
+    if (!c->have_sequences && !c->arena_pending) return fail(c, APD_ERR_STATE, "no sequence batch declared");
+    *d_arena = c->d_arena;
+    *n_floats = (uint64_t)c->arena.total_frames * c->arena.dpad;
+    return APD_OK;
+}
+
+apd_status apd_arena_commit(apd_ctx* c)
+{
+    if (!c) return APD_ERR_INVALID;
+    if (!c->arena_pending) return fail(c, APD_ERR_STATE, "apd_set_sequences_layout has not been called");
+    c->arena_pending = false;
     c->have_sequences = true;
     return APD_OK;
 }

@@ -131,6 +131,19 @@ apd_status apd_set_sequences_encoded(apd_ctx *ctx, const float *const *cepstra, 
                                      const float *b_encode, uint32_t n_latent);
 apd_status apd_get_sequence(apd_ctx *ctx, uint32_t index, float *out, uint64_t cap_floats);
 
+/* One-process-per-GPU jobs: every rank declares the same batch, ONE rank uploads it with apd_set_sequences and the
+ * others receive the packed arena over NVLink (ncclBroadcast) instead of packing and uploading it again:
+ *   apd_set_sequences_layout  the batch's lengths and frame width only -- builds the same arena layout and tables every
+ *                             rank derives from them, allocates the arena, leaves its contents undefined;
+ *   apd_arena_device          the arena's device pointer and size in floats (also valid after apd_set_sequences on the
+ *                             uploading rank, once apd_synchronize(ctx, 0) has returned);
+ *   apd_arena_commit          the caller has filled the arena, in stream order before any later call that names the
+ *                             same stream (or synchronised): the batch is ready.
+ * The layout is a pure function of (lens, dim), so the arenas of all ranks are byte-identical. */
+apd_status apd_set_sequences_layout(apd_ctx *ctx, const uint32_t *lens, uint32_t n, uint32_t dim);
+apd_status apd_arena_device(apd_ctx *ctx, void **d_arena, uint64_t *n_floats);
+apd_status apd_arena_commit(apd_ctx *ctx);
+
 /* Multi-process sharding (one process per GPU, e.g. under torchrun): this
  * context computes work units u with u % world == rank.  Default 0 / 1. */
 apd_status apd_set_shard(apd_ctx *ctx, uint32_t rank, uint32_t world);

@@ -81,6 +81,9 @@ extern "C" {
     pub fn apd_set_sequences_encoded(ctx: *mut apd_ctx, cepstra: *const *const f32, lens: *const u32, n: u32, n_bins: u32,
                                      w_encode: *const f32, b_encode: *const f32, n_latent: u32) -> c_int;
     pub fn apd_get_sequence(ctx: *mut apd_ctx, index: u32, out: *mut f32, cap_floats: u64) -> c_int;
+    pub fn apd_set_sequences_layout(ctx: *mut apd_ctx, lens: *const u32, n: u32, dim: u32) -> c_int;
+    pub fn apd_arena_device(ctx: *mut apd_ctx, d_arena: *mut *mut c_void, n_floats: *mut u64) -> c_int;
+    pub fn apd_arena_commit(ctx: *mut apd_ctx) -> c_int;
     pub fn apd_set_shard(ctx: *mut apd_ctx, rank: u32, world: u32) -> c_int;
     pub fn apd_align_all(ctx: *mut apd_ctx, p: *const apd_params, out_nxn: *mut f32) -> c_int;
     pub fn apd_packed_len(ctx: *mut apd_ctx, p: *const apd_params, n_floats: *mut u64) -> c_int;
