@@ -142,3 +142,67 @@ def test_all_ranks_walk_the_same_collectives(world, workload):
     assert d["e2e"]["value"] > 0 and d["other_mode"]["gcups"] > 0 and d["threshold_select"]["threshold"] == 1.0
     assert d["gpu_launches"] > 0
     assert len(d["matrix_checksum_u64"]) == 16 and d["parity_checked"] == 256 and d["e2e_cold"]["value"] > 0
+
+
+class _StubGroupCtx:
+    peer_stores = True
+
+    def launch_plan(self):
+        return [{"ring": "tmem", "ring_tiles": 31, "units": 1, "ctas": 1, "warps_per_cta": 4, "ctas_per_sm": 2, "smem_bytes": 0}]
+
+
+class StubGroupAligner:
+    """Call surface of distributed.GroupAligner (the one-process, many-GPU form)."""
+
+    def __init__(self, seqs, devices="all", mode=0):
+        self.n = len(seqs)
+        self.ctx = _StubGroupCtx()
+        self.world = len(devices)
+
+    def set_sequences(self, seqs):
+        self.n = len(seqs)
+
+    def align_all(self, pct, ins=1.0, dele=1.0, mat=1.0, out=None):
+        out[...] = 0.0
+        return out
+
+    def percentile_of_matrix(self, perc):
+        return np.float32(1.0)
+
+    def stats(self):
+        return {"cells_reference": 5000, "cells_computed": 5500, "kernel_ms": 1.0, "scatter_ms": 0.1, "kernel_launches": 4,
+                "sm_count": 148, "h2d_bytes": 10, "select_ms": 0.5, "units_local": 2, "units_total": 2}
+
+    def close(self):
+        pass
+
+
+def test_single_process_arm_emits_the_contract_line(monkeypatch, capsys):
+    """`bench.py --single-process --gpus N` (the in-library device group) on the CPU with a stub in place of the
+    library: one JSON line with the contract keys plus the evidence keys."""
+    import bench
+    import audio_pattern_discovery_b200 as pkg
+    import audio_pattern_discovery_b200.distributed as D
+    lines = []
+    monkeypatch.setattr(D, "GroupAligner", StubGroupAligner)
+    monkeypatch.setattr(pkg, "visible_devices", lambda: 4)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(bench, "emit", lambda line: lines.append(line))
+    monkeypatch.setattr(bench.ClockSampler, "start", lambda self: None)
+    monkeypatch.setattr(bench.ClockSampler, "stop", lambda self: {"sm_mhz": None, "sm_max_mhz": None, "reasons": []})
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "4", "--single-process", "--seqs", "24", "--steps", "2",
+                                      "--warmup", "1", "--no-cpu"])
+    saved = os.dup(1)                       # bench.main() points fd 1 at stderr for the rest of the process
+    try:
+        assert bench.main() == 0
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+    assert len(lines) == 1
+    d = lines[0]
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "e2e_cold", "gpu_launches", "roofline", "clocks",
+                "matrix_checksum_u64", "parity_checked", "launch_form"):
+        assert key in d, key
+    assert d["n_gpus"] == 4 and d["gpu_launches"] > 0 and "apd_create_multi" in d["launch_form"]
+    assert d["parity_ok"] is False          # the stub's all-zero matrix cannot match the oracle: the check is live
